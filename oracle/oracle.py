@@ -1,0 +1,426 @@
+"""CPU ORACLE (Python side) for the miRge2.0 annotate-mode read pipeline.
+
+TEST INFRASTRUCTURE ONLY -- only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.  Nothing under
+mirge_b200/ does.
+
+PARITY UNPINNED: the reference ships no golden vectors and its engines
+(cutadapt 1.16, bowtie 1.1.2) are not installable here; see mirge_oracle.c.
+
+Two layers:
+  * ctypes bindings to libmirge_oracle.so (trim / collapse / mapping rounds /
+    integer tallies), and
+  * literal Python-3 restatements of the reference's dict-based host stages
+    (quantReads -> seqDic, summarize, miRNAmerge, filter and the CSV writers),
+    each citing the reference file:line it follows, so whole-table parity can
+    be checked end to end.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+LIB_IDS = {'mirna': 0, 'hairpin': 1, 'mature_trna': 2, 'pre_trna': 3, 'snorna': 4,
+           'rrna': 5, 'ncrna_others': 6, 'mrna': 7, 'spike-in': 9}
+
+
+def build():
+    """Compile libmirge_oracle.so (building the checker is not using it)."""
+    subprocess.check_call(['make', '-s', '-C', _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, 'libmirge_oracle.so')
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_new.restype = C.c_void_p
+        L.orc_new.argtypes = [C.c_int, C.c_int]
+        L.orc_free.argtypes = [C.c_void_p]
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_last_error.argtypes = [C.c_void_p]
+        L.orc_set_adapter.argtypes = [C.c_void_p, C.c_char_p]
+        L.orc_detect_phred.argtypes = [C.c_char_p, C.c_uint64]
+        L.orc_feed_fastq.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_int, C.c_int]
+        L.orc_trim_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_n_unique.restype = C.c_uint64
+        L.orc_n_unique.argtypes = [C.c_void_p]
+        L.orc_seq_bytes.restype = C.c_uint64
+        L.orc_seq_bytes.argtypes = [C.c_void_p]
+        L.orc_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_load_lib.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int]
+        L.orc_annotate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_export.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        L.orc_len_hist.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_tally.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_quality_trim_index.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_locate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
+        L.orc_locate_unbanded.argtypes = L.orc_locate.argtypes
+        L.orc_map_one.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_map_bruteforce.argtypes = L.orc_map_one.argtypes
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# --------------------------------------------------------------------------
+# scalar entry points (known-answer tests)
+# --------------------------------------------------------------------------
+def quality_trim_index(qual, cutoff_front, cutoff_back, base=33):
+    out = np.zeros(2, np.int32)
+    q = qual.encode() if isinstance(qual, str) else qual
+    lib().orc_quality_trim_index(q, len(q), cutoff_front, cutoff_back, base, _p(out[0:1]), _p(out[1:2]))
+    return int(out[0]), int(out[1])
+
+
+def locate(adapter, read, max_error_rate=0.12, min_overlap=3, banded=True):
+    """Aligner.locate for a BACK adapter -> (astart, astop, rstart, rstop, matches, errors) or None."""
+    out = np.zeros(6, np.int32)
+    a, r = adapter.encode(), read.encode()
+    f = lib().orc_locate if banded else lib().orc_locate_unbanded
+    ok = f(a, len(a), r, len(r), max_error_rate, min_overlap, _p(out))
+    return tuple(int(x) for x in out) if ok else None
+
+
+def py_locate(adapter, read, max_error_rate=0.12, min_overlap=3):
+    """Pure-Python twin of mirge_oracle.c:orc_locate (cutadapt _align.pyx locate, BACK)."""
+    m, n = len(adapter), len(read)
+    k = int(max_error_rate * m)
+    col = [[i, 0, 0] for i in range(m + 1)]  # cost, origin, matches
+    best = dict(ref_stop=m, query_stop=n, cost=m + n, origin=0, matches=0)
+    last = min(m, k + 1)
+    for j in range(1, n + 1):
+        tmp = list(col[0])
+        col[0][1] = j
+        for i in range(1, last + 1):
+            if adapter[i - 1] == read[j - 1]:
+                cost, origin, matches = tmp[0], tmp[1], tmp[2] + 1
+            else:
+                cd, cdel, cins = tmp[0] + 1, col[i][0] + 1, col[i - 1][0] + 1
+                if cd <= cdel and cd <= cins:
+                    cost, origin, matches = cd, tmp[1], tmp[2]
+                elif cins <= cdel:
+                    cost, origin, matches = cins, col[i - 1][1], col[i - 1][2]
+                else:
+                    cost, origin, matches = cdel, col[i][1], col[i][2]
+            tmp = list(col[i])
+            col[i] = [cost, origin, matches]
+        while last >= 0 and col[last][0] > k:
+            last -= 1
+        if last < m:
+            last += 1
+        else:
+            length = m + min(col[m][1], 0)
+            cost, matches = col[m][0], col[m][2]
+            if length >= min_overlap and cost <= length * max_error_rate and (
+                    matches > best['matches'] or (matches == best['matches'] and cost < best['cost'])):
+                best.update(matches=matches, cost=cost, origin=col[m][1], ref_stop=m, query_stop=j)
+                if cost == 0 and matches == m:
+                    break
+    for i in range(m, -1, -1):
+        length = i + min(col[i][1], 0)
+        cost, matches = col[i][0], col[i][2]
+        if length >= min_overlap and cost <= length * max_error_rate and (
+                matches > best['matches'] or (matches == best['matches'] and cost < best['cost'])):
+            best.update(matches=matches, cost=cost, origin=col[i][1], ref_stop=i, query_stop=n)
+    if best['cost'] == m + n:
+        return None
+    return (0, best['ref_stop'], best['origin'], best['query_stop'], best['matches'], best['cost'])
+
+
+# --------------------------------------------------------------------------
+# pipeline object
+# --------------------------------------------------------------------------
+class Oracle:
+    def __init__(self, n_samples=1, spike_in=False, adapter='none', threads=0):
+        self.S = n_samples
+        self.spike_in = bool(spike_in)
+        self.threads = threads or (os.cpu_count() or 1)
+        self.h = lib().orc_new(n_samples, int(self.spike_in))
+        self.lib_names = {}
+        self.set_adapter(adapter)
+
+    def close(self):
+        if self.h:
+            lib().orc_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(lib().orc_last_error(self.h).decode())
+
+    def set_adapter(self, spec):
+        self._check(lib().orc_set_adapter(self.h, spec.encode()))
+
+    @staticmethod
+    def detect_phred(buf):
+        return lib().orc_detect_phred(buf, len(buf))
+
+    def feed_fastq(self, sample, buf, phred_base=None):
+        if phred_base is None:
+            phred_base = self.detect_phred(buf)
+        self._check(lib().orc_feed_fastq(self.h, sample, buf, len(buf), phred_base, self.threads))
+        return phred_base
+
+    def trim_fastq(self, buf, phred_base=33, max_rec=None):
+        max_rec = max_rec or (buf.count(b'\n') // 4 + 1)
+        st = np.zeros(max_rec, np.int32)
+        sp = np.zeros(max_rec, np.int32)
+        n = lib().orc_trim_fastq(self.h, buf, len(buf), phred_base, _p(st), _p(sp), max_rec)
+        return st[:n], sp[:n]
+
+    def stats(self):
+        a = np.zeros(self.S, np.uint64)
+        b = np.zeros(self.S, np.uint64)
+        lib().orc_stats(self.h, _p(a), _p(b))
+        return a, b
+
+    def load_library(self, lib_id, names, seqs):
+        off = np.zeros(len(seqs) + 1, np.uint64)
+        off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+        cat = ''.join(seqs).encode()
+        self._check(lib().orc_load_lib(self.h, lib_id, cat, _p(off), len(seqs)))
+        self.lib_names[lib_id] = list(names)
+
+    def annotate(self):
+        rp = np.zeros(10, np.uint64)
+        ra = np.zeros(10, np.uint64)
+        self._check(lib().orc_annotate(self.h, self.threads, _p(rp), _p(ra)))
+        return rp, ra
+
+    def map_one(self, lib_id, read, mode, param, highest=False, brute=False):
+        r = np.zeros(3, np.int32)
+        f = lib().orc_map_bruteforce if brute else lib().orc_map_one
+        ok = f(self.h, lib_id, read.encode(), len(read), mode, param, int(highest), _p(r[0:1]), _p(r[1:2]), _p(r[2:3]))
+        return (int(r[0]), int(r[1]), int(r[2])) if ok else None
+
+    def export(self):
+        U = int(lib().orc_n_unique(self.h))
+        nb = int(lib().orc_seq_bytes(self.h))
+        seqs = np.zeros(max(nb, 1), np.uint8)
+        off = np.zeros(U, np.uint64)
+        ln = np.zeros(U, np.uint32)
+        cnt = np.zeros((U, self.S), np.uint32)
+        ro = np.zeros(U, np.int32)
+        rf = np.zeros(U, np.int32)
+        ps = np.zeros(U, np.int32)
+        mm = np.zeros(U, np.int32)
+        lib().orc_export(self.h, _p(seqs), _p(off), _p(ln), _p(cnt), _p(ro), _p(rf), _p(ps), _p(mm))
+        raw = seqs.tobytes()
+        strs = [raw[int(o):int(o) + int(l)].decode() for o, l in zip(off, ln)]
+        return dict(seqs=strs, counts=cnt, round_of=ro, ref_of=rf, pos_of=ps, mm_of=mm)
+
+    def len_hist(self, max_len=256):
+        out = np.zeros((max_len + 1, self.S), np.uint64)
+        lib().orc_len_hist(self.h, _p(out), max_len)
+        return out
+
+    def tally(self):
+        nmir = len(self.lib_names.get(0, []))
+        q = np.zeros((nmir, self.S), np.int64)
+        i = np.zeros((nmir, self.S), np.int64)
+        t = np.zeros((self.S, 12), np.int64)
+        lib().orc_tally(self.h, _p(q), _p(i), _p(t))
+        return q, i, t
+
+    # -- reference-shaped dicts ------------------------------------------------
+    def seqDic(self):
+        """seqDic as built by quantReads.py:9-16 and filled by updateAnnotDic
+        (runAnnotationPipeline.py:341-352): seq -> {'quant','annot','length'}."""
+        e = self.export()
+        nslots = 11 if self.spike_in else 10
+        round_lib = [0, 1, 2, 3, 4, 5, 6, 7, 0, 9]
+        d = {}
+        for k, s in enumerate(e['seqs']):
+            annot = [0] + [''] * (nslots - 1)
+            ro = int(e['round_of'][k])
+            if ro:
+                annot[0] = 1
+                annot[ro] = self.lib_names[round_lib[ro - 1]][int(e['ref_of'][k])]
+            d[s] = {'quant': [int(x) for x in e['counts'][k]], 'annot': annot, 'length': len(s)}
+        return d
+
+
+# --------------------------------------------------------------------------
+# literal restatements of the reference's dict-based host stages
+# --------------------------------------------------------------------------
+def py2_str_float(x):
+    """Python 2 str(float): repr with 12 significant digits, '.0' kept."""
+    s = '%.12g' % x
+    if '.' not in s and 'e' not in s and 'n' not in s and 'i' not in s:
+        s += '.0'
+    return s
+
+
+def summarize(seqDic, sampleList, logDic, mirDic, mirList, spikeIn):
+    """summarize.py:3-66; mirList stands in for `bowtie-inspect -n` (:6-9)."""
+    for name in mirList:
+        mirDic[name] = {'quant': [0] * len(sampleList), 'iscan': [0] * len(sampleList)}
+    keys = ['trimmedUniq', 'mirnaReads', 'hairpinReads', 'maturetrnaReads', 'pretrnaReads', 'snornaReads',
+            'rrnaReads', 'ncrnaOthersReads', 'mrnaReads', 'remReads']
+    for i in range(len(sampleList)):
+        for k in keys:
+            logDic['quantStats'][i][k] = 0
+        if spikeIn:
+            logDic['quantStats'][i]['spikeInReads'] = 0
+    for seqKey in seqDic:
+        e = seqDic[seqKey]
+        for i in range(len(sampleList)):
+            q = e['quant'][i]
+            if q != 0:
+                st = logDic['quantStats'][i]
+                st['trimmedUniq'] += 1
+                a = e['annot']
+                if a[1] != '' or a[9] != '':
+                    st['mirnaReads'] += q
+                    if a[1] != '':
+                        mirDic[a[1]]['quant'][i] += q
+                        mirDic[a[1]]['iscan'][i] += q
+                    else:
+                        mirDic[a[9]]['quant'][i] += q
+                elif a[2] != '':
+                    st['hairpinReads'] += q
+                elif a[3] != '':
+                    st['maturetrnaReads'] += q
+                elif a[4] != '':
+                    st['pretrnaReads'] += q
+                elif a[5] != '':
+                    st['snornaReads'] += q
+                elif a[6] != '':
+                    st['rrnaReads'] += q
+                elif a[7] != '':
+                    st['ncrnaOthersReads'] += q
+                elif a[8] != '':
+                    st['mrnaReads'] += q
+                else:
+                    if spikeIn and a[10] != '':
+                        st['spikeInReads'] += q
+                    else:
+                        st['remReads'] += q
+
+
+def miRNAmerge(merge_lines, sampleList, mirDic):
+    """miRNAmerge.py:13-41 (merge_lines = rows of <sp>_merges_<DB>.csv)."""
+    delList = []
+    for line in merge_lines:
+        c = line.strip().split(',')
+        for i in range(1, len(c)):
+            for j in range(len(sampleList)):
+                try:
+                    if mirDic[c[i]]['quant'][j] > 0:
+                        try:
+                            mirDic[c[0]]['quant'][j] = mirDic[c[0]]['quant'][j] + mirDic[c[i]]['quant'][j]
+                            mirDic[c[0]]['iscan'][j] = mirDic[c[0]]['iscan'][j] + mirDic[c[i]]['iscan'][j]
+                        except KeyError:
+                            mirDic[c[0]] = {'quant': [0] * len(sampleList), 'iscan': [0] * len(sampleList)}
+                            mirDic[c[0]]['quant'][j] = mirDic[c[i]]['quant'][j]
+                            mirDic[c[0]]['iscan'][j] = mirDic[c[i]]['iscan'][j]
+                    delList.append(c[i])
+                except KeyError:
+                    pass
+    for item in set(delList):
+        mirDic.pop(item, None)
+
+
+class ZeroMiRNA(Exception):
+    """filter.py:25-32 aborts (sys.exit(1)) when a sample has no miRNA reads."""
+
+
+def filter_(mirDic, sampleList, logDic, canoRatioTmp):
+    """filter.py:3-32."""
+    thr = float(canoRatioTmp)
+    for k in mirDic:
+        for i in range(len(sampleList)):
+            try:
+                v = float(mirDic[k]['iscan'][i]) / mirDic[k]['quant'][i]
+            except ZeroDivisionError:
+                v = 1.1
+            if mirDic[k]['iscan'][i] < 2 or v < thr:
+                mirDic[k]['quant'][i] = 0
+    for k in mirDic:
+        for i in range(len(sampleList)):
+            if mirDic[k]['quant'][i] > 0:
+                st = logDic['quantStats'][i]
+                st['mirnaReadsFiltered'] = st.get('mirnaReadsFiltered', 0) + mirDic[k]['quant'][i]
+                st['mirnaUniqFiltered'] = st.get('mirnaUniqFiltered', 0) + 1
+    for i in range(len(sampleList)):
+        if logDic['quantStats'][i].get('mirnaReadsFiltered', 0) == 0:
+            raise ZeroMiRNA(sampleList[i])
+
+
+def annotation_report_csv(sampleList, logDic, spikeIn):
+    """generateReport.py:106-108,191-201 (CSV only)."""
+    out = ['File name(s),Total Input Reads,Trimmed Reads(all),Trimmed Reads(unique),All miRNA Reads,Filtered miRNA Reads,'
+           'Unique miRNAs,Hairpin miRNAs,mature tRNA Reads,primary tRNA Reads,snoRNA Reads,rRNA Reads,ncRNA others,'
+           'mRNA Reads,Remaining Reads\n']
+    for i, s in enumerate(sampleList):
+        st = logDic['quantStats'][i]
+        keys = ['totalReads', 'trimmedReads', 'trimmedUniq', 'mirnaReads', 'mirnaReadsFiltered', 'mirnaUniqFiltered',
+                'hairpinReads', 'maturetrnaReads', 'pretrnaReads', 'snornaReads', 'rrnaReads', 'ncrnaOthersReads', 'mrnaReads']
+        if spikeIn:
+            keys.append('spikeInReads')
+        keys.append('remReads')
+        out.append(s + ',' + ','.join(str(st[k]) for k in keys) + '\n')
+    return ''.join(out)
+
+
+def mir_counts_csv(sampleList, logDic, mirDic):
+    """writeDataToCSV.py:1190-1205."""
+    out = ['miRNA' + ''.join(',' + s for s in sampleList) + '\n']
+    out.append('miRNAtotal' + ''.join(',' + str(logDic['quantStats'][i]['mirnaReadsFiltered']) for i in range(len(sampleList))) + '\n')
+    for k in sorted(mirDic.keys()):
+        out.append(k + ''.join(',' + str(mirDic[k]['quant'][i]) for i in range(len(sampleList))) + '\n')
+    return ''.join(out)
+
+
+def mir_rpm_csv(sampleList, logDic, mirDic):
+    """writeDataToCSV.py:1207-1219."""
+    out = ['miRNA' + ''.join(',' + s for s in sampleList) + '\n']
+    for k in sorted(mirDic.keys()):
+        row = k
+        for i in range(len(sampleList)):
+            t = logDic['quantStats'][i]['mirnaReadsFiltered']
+            row += (',' + py2_str_float(1000000.0 * mirDic[k]['quant'][i] / t)) if t > 0 else ',0'
+        out.append(row + '\n')
+    return ''.join(out)
+
+
+def mapped_unmapped_rows(seqDic, spikeIn):
+    """writeDataToCSV.py:582-619,1172-1188 -> (mapped row set, unmapped row set)."""
+    n = 11 if spikeIn else 10
+    mapped, unmapped = set(), set()
+    for s, e in seqDic.items():
+        row = ','.join([s] + [str(e['annot'][i]) for i in range(n)] + [str(q) for q in e['quant']])
+        (mapped if e['annot'][0] > 0 else unmapped).add(row)
+    return mapped, unmapped
+
+
+def run_tables(o, sampleList, mirna_names, merge_lines, canoRatio='0.1'):
+    """__main__.py:375-389 after the GPU-replaceable part: summarize -> merge -> filter -> tables."""
+    seqDic = o.seqDic()
+    proc, kept = o.stats()
+    logDic = {'quantStats': [{'filename': s, 'totalReads': int(proc[i]), 'trimmedReads': int(kept[i])}
+                             for i, s in enumerate(sampleList)], 'annotStats': []}
+    mirDic = {}
+    summarize(seqDic, sampleList, logDic, mirDic, mirna_names, o.spike_in)
+    miRNAmerge(merge_lines, sampleList, mirDic)
+    filter_(mirDic, sampleList, logDic, canoRatio)
+    return dict(seqDic=seqDic, logDic=logDic, mirDic=mirDic,
+                report=annotation_report_csv(sampleList, logDic, o.spike_in),
+                counts=mir_counts_csv(sampleList, logDic, mirDic),
+                rpm=mir_rpm_csv(sampleList, logDic, mirDic))
