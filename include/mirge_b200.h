@@ -1,0 +1,152 @@
+/*
+ * mirge_b200.h -- C ABI of the B200-native miRge2.0 annotate-mode hot path.
+ *
+ * The reference (mhalushka/miRge, Python 2) has no FFI: its hot path is reached
+ * through Python function boundaries and through process/file boundaries to
+ * cutadapt and bowtie.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/src/mirge).  Plain pointers and
+ * sizes only; one context per process per GPU; not thread-safe.  Every function
+ * returns 0 on success or a negative MIRGE_E_* code, with a message available
+ * from mirge_last_error().  Caller-owned buffers are never freed or retained.
+ */
+#ifndef MIRGE_B200_H
+#define MIRGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mirge_ctx mirge_ctx;
+
+enum {
+    MIRGE_OK = 0,
+    MIRGE_E_ARG = -1,       /* bad argument */
+    MIRGE_E_CUDA = -2,      /* CUDA runtime error */
+    MIRGE_E_FORMAT = -3,    /* FASTQ format error (cutadapt FormatError) */
+    MIRGE_E_TOOLONG = -4,   /* a read exceeds max_read_len */
+    MIRGE_E_FULL = -5,      /* unique-sequence table full (raise max_unique) */
+    MIRGE_E_STATE = -6      /* call order violated */
+};
+
+/* Library slots; rounds use them in the order of
+ * utils/runAnnotationPipeline.py:588-599 (spike-in variant :574-586). */
+enum {
+    MIRGE_LIB_MIRNA = 0, MIRGE_LIB_HAIRPIN = 1, MIRGE_LIB_MATURE_TRNA = 2, MIRGE_LIB_PRE_TRNA = 3,
+    MIRGE_LIB_SNORNA = 4, MIRGE_LIB_RRNA = 5, MIRGE_LIB_NCRNA_OTHERS = 6, MIRGE_LIB_MRNA = 7,
+    MIRGE_LIB_SPIKEIN = 9, MIRGE_N_LIBS = 10
+};
+
+#define MIRGE_N_ROUNDS 10       /* 9 rounds, 10 with -spikeIn */
+#define MIRGE_N_TOTALS 12       /* columns of lib_totals, see mirge_export_tables */
+
+/* -- context ------------------------------------------------------------- */
+
+/* Replaces the four dicts main() owns (__main__.py:318-330: seqDic, mirDic,
+ * readLengthDic, logDic) with device-resident state on CUDA device `device`.
+ * max_unique bounds the number of distinct trimmed sequences; max_read_len
+ * (<= 128) bounds the raw read length. */
+int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, int max_read_len, mirge_ctx **out);
+void mirge_destroy(mirge_ctx *ctx);
+const char *mirge_last_error(const mirge_ctx *ctx);
+
+/* Run all work on an existing cudaStream_t (passed as void*); default is a
+ * private non-blocking stream. */
+int mirge_set_stream(mirge_ctx *ctx, void *cuda_stream);
+/* Wait for queued work and surface device-side error flags. */
+int mirge_sync(mirge_ctx *ctx);
+
+/* -- stage 1: trim + quality/length filter + collapse ------------------- */
+
+/* Worker.__init__ (utils/trim_file.py:24-41): spec is the `adapter` string
+ * trim_file receives -- "none", "+N" (UnconditionalCutter) or one or more
+ * comma-separated 3' adapters (ACGT only, each <= 64 nt);
+ * error_rate 0.12 (:32), min_overlap 3 (cutadapt default), min_length 16 (:33),
+ * qual_cutoff 10 (:30). */
+int mirge_set_adapter(mirge_ctx *ctx, const char *spec, double error_rate, int min_overlap, int min_length, int qual_cutoff);
+
+/* Quality base auto-detection as it takes effect in trim_file (:104-109):
+ * 64 iff the FIRST read holds a quality character > 'J'.  Host-side, pure. */
+int mirge_detect_phred(const char *fastq, uint64_t nbytes);
+
+/* trim_file(infile, adapter, outfile, threads, phred) (utils/trim_file.py:89)
+ * fused with quantReads(...) (utils/quantReads.py:3-24) for one record-aligned
+ * chunk of FASTQ text (4-line records) of sample `sample`:  H2D copy, parse and
+ * 2-bit pack (K0), then 3' quality trim, 3' adapter removal, length filter and
+ * insertion into the device hash table of unique sequences (K1).  No trimmed
+ * FASTQ is written.  Asynchronous on the context's stream; `fastq` must stay
+ * valid until mirge_sync() unless it is pageable memory. */
+int mirge_feed_fastq(mirge_ctx *ctx, int sample, const char *fastq, uint64_t nbytes, int phred_base);
+/* Same, FASTQ text already resident in device memory (16-byte aligned). */
+int mirge_feed_fastq_device(mirge_ctx *ctx, int sample, const void *fastq_dev, uint64_t nbytes, int phred_base);
+
+/* (processed, kept) per sample as returned by trim_file (:134) and the number
+ * of unique sequences (len(seqDic)).  Synchronises. */
+int mirge_get_stats(mirge_ctx *ctx, uint64_t *processed, uint64_t *kept, uint64_t *n_unique);
+
+/* -- stage 2: mapping rounds --------------------------------------------- */
+
+/* Stands in for the bowtie index files main() resolves (__main__.py:262-281):
+ * n_refs entries, sequences concatenated as ASCII with offsets[n_refs+1].
+ * Names stay with the caller; kernels speak reference indices.  Builds the
+ * 2-bit reference and its k-mer seed tables on the device. */
+int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_ascii, const uint64_t *offsets);
+
+/* runAnnotationPipeline(...) (utils/runAnnotationPipeline.py:566,636-705): all
+ * rounds in order over the still un-annotated unique sequences, including the
+ * poly-T pre-tRNA round (:664-704). */
+int mirge_annotate(mirge_ctx *ctx);
+
+/* -- stage 3: tallies ----------------------------------------------------- */
+
+/* summarize(...) integer part (utils/summarize.py:34-66). */
+int mirge_tally(mirge_ctx *ctx);
+
+/* -- export ---------------------------------------------------------------- */
+
+/* seqDic (__main__.py:318-321): for unique u < n_unique, seq[u*stride ..] holds
+ * the ASCII sequence (no terminator), len[u] its length, counts[u*S+s] the
+ * per-sample read count, round_of[u] = 0 (un-annotated) or round index + 1 as in
+ * annot[] (runAnnotationPipeline.py:345), ref_of/pos_of the reference entry and
+ * 0-based offset of the reported hit (for round 9/isomiR: of the -5 1 -3 2
+ * trimmed read), mm_of its mismatch count.  Any pointer may be NULL. */
+int mirge_export_unique(mirge_ctx *ctx, uint64_t cap, int stride, char *seq, uint8_t *len, uint32_t *counts,
+                        int8_t *round_of, int32_t *ref_of, int32_t *pos_of, int8_t *mm_of);
+
+/* mir_quant / mir_iscan: [n_mirna_refs][S] (mirDic 'quant' / 'iscan' before
+ * merge+filter).  lib_totals: [S][12] = trimmedUniq, mirnaReads, hairpinReads,
+ * maturetrnaReads, pretrnaReads, snornaReads, rrnaReads, ncrnaOthersReads,
+ * mrnaReads, spikeInReads, remReads, (unused)  (logDic['quantStats']).
+ * len_hist: [max_read_len+1][S] (readLengthDic, quantReads.py:17-21).
+ * round_processed / round_aligned: [10] (parseBowtieLog, :9-18). */
+int mirge_export_tables(mirge_ctx *ctx, int64_t *mir_quant, int64_t *mir_iscan, int64_t *lib_totals,
+                        uint64_t *len_hist, uint64_t *round_processed, uint64_t *round_aligned);
+
+/* -- multi-GPU exchange (no reference counterpart; samples are serial there) */
+
+/* Bytes of one exchange record: packed key + length + S counts. */
+int mirge_record_bytes(const mirge_ctx *ctx);
+/* Write every unique sequence as a record into dev_buf, grouped by owner
+ * rank = hash(key) % n_parts; part_counts[n_parts] (host) receives the group
+ * sizes.  Synchronises. */
+int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint64_t cap_records, uint64_t *part_counts);
+/* Forget all unique sequences (per-sample processed/kept and len_hist stay). */
+int mirge_reset_unique(mirge_ctx *ctx);
+/* Insert n_records received records, adding their counts. */
+int mirge_import_records_device(mirge_ctx *ctx, const void *dev_buf, uint64_t n_records);
+/* Owner hash of an ASCII sequence (for host-side tests of the partitioning). */
+uint64_t mirge_hash_sequence(const char *seq, int len);
+
+/* -- measurement ----------------------------------------------------------- */
+
+/* Per-kernel CUDA-event timing on the context's stream. */
+#define MIRGE_N_KERNELS 16
+int mirge_profile_enable(mirge_ctx *ctx, int on);
+/* ms[k], launches[k] accumulated since enable; names[k] static strings. */
+int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const char **names);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIRGE_B200_H */

@@ -1,0 +1,725 @@
+// capi.cu -- context management and the extern "C" entry points declared in
+// include/mirge_b200.h.  Host-side plumbing only; the kernels live in
+// k0_parse.cuh (FASTQ -> packed records), k1_trim.cuh (trim + collapse),
+// k2_map.cuh (mapping rounds) and k3_tally.cuh (segmented tallies).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <ctype.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mirge_b200.h"
+#include "common.cuh"
+#include "scan.cuh"
+#include "k0_parse.cuh"
+#include "k1_trim.cuh"
+#include "k2_map.cuh"
+#include "k3_tally.cuh"
+
+enum KernelId {
+    KID_K0_COUNT = 0, KID_K0_SCAN, KID_K0_LINES, KID_K0_PACK, KID_K1_TRIM, KID_K2_ROUND, KID_K3_KEYS, KID_K3_SORT,
+    KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_N
+};
+static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
+    "k0_count_newlines", "k0_scan", "k0_line_starts", "k0_pack", "k1_trim_collapse", "k2_round", "k3_make_keys",
+    "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "", ""};
+
+struct DevLib {
+    u64 *seq = nullptr, *amb = nullptr;
+    u32 *ref_off = nullptr;
+    int n_refs = 0;
+    u32 total = 0;
+    int ntabs = 0;
+    int tab_k[K2_MAX_TABS];
+    u32 *tab_off[K2_MAX_TABS];
+    u32 *tab_pos[K2_MAX_TABS];
+};
+
+struct ProfSpan { int kid; cudaEvent_t a, b; };
+
+struct mirge_ctx {
+    int device = 0, S = 1, spike_in = 0, W = 2, max_len = 64;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    // trim configuration
+    TrimParams tp;
+    int qual_cutoff = 10;
+    // K0 scratch
+    unsigned char *d_text = nullptr; size_t text_cap = 0;
+    u32 *d_tile = nullptr; size_t tile_cap = 0;
+    u32 *d_scan = nullptr; size_t scan_cap = 0;
+    u32 *d_lines = nullptr; size_t lines_cap = 0;
+    u64 *d_bases = nullptr, *d_nmask = nullptr; u32 *d_meta = nullptr; size_t rec_cap = 0;
+    // unique table
+    void *d_slots = nullptr; u64 table_cap = 0;
+    u64 max_unique = 0;
+    u64 *d_useq = nullptr, *d_unmask = nullptr; u8 *d_ulen = nullptr; u32 *d_counts = nullptr;
+    signed char *d_round_of = nullptr, *d_mm_of = nullptr; int *d_ref_of = nullptr, *d_pos_of = nullptr;
+    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept
+    u64 *d_ctr = nullptr;
+    u64 *d_len_hist = nullptr;
+    std::vector<u64> processed;
+    // mapping
+    DevLib libs[MIRGE_N_LIBS];
+    u32 *d_todo[2] = {nullptr, nullptr};
+    u64 *d_todo_n = nullptr;        // [MIRGE_N_ROUNDS + 1]
+    u64 *d_round_stats = nullptr;   // [2][MIRGE_N_ROUNDS]
+    bool annotated = false;
+    // tallies
+    i64 *d_mir_quant = nullptr, *d_mir_iscan = nullptr, *d_lib_totals = nullptr;
+    int tally_nmir = -1;
+    bool tallied = false;
+    // profiling
+    bool prof = false;
+    std::vector<ProfSpan> spans;
+    double prof_ms[MIRGE_N_KERNELS];
+    uint64_t prof_n[MIRGE_N_KERNELS];
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = b_;                                                                         \
+            return MIRGE_E_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+static int fail(mirge_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
+
+struct ProfScope {
+    mirge_ctx *c; int kid; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(mirge_ctx *c_, int kid_) : c(c_), kid(kid_)
+    {
+        if (c->prof) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+    }
+    ~ProfScope()
+    {
+        if (c->prof) { cudaEventRecord(b, c->stream); c->spans.push_back({kid, a, b}); }
+    }
+};
+
+template <typename T>
+static cudaError_t ensure(T **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    size_t n = need + need / 8 + 64;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e == cudaSuccess) *cap = n;
+    return e;
+}
+
+static int grid_for(u64 n, int threads, int max_blocks)
+{
+    u64 b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > (u64)max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+template <int W>
+static TableView<W> table_view(mirge_ctx *c)
+{
+    TableView<W> T;
+    T.slots = (TEntry<W> *)c->d_slots; T.mask = c->table_cap - 1;
+    T.useq = c->d_useq; T.unmask = c->d_unmask; T.ulen = c->d_ulen; T.counts = c->d_counts;
+    T.max_unique = c->max_unique; T.n_unique = c->d_ctr; T.err = (u32 *)(c->d_ctr + 1); T.S = c->S;
+    return T;
+}
+
+// Definitions below take C linkage from their declarations in mirge_b200.h.
+
+const char *mirge_last_error(const mirge_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, int max_read_len, mirge_ctx **out)
+{
+    if (!out || n_samples < 1 || max_unique < 1 || max_unique > 0xFFFFFFF0ull || max_read_len < 1 || max_read_len > 128) {
+        g_create_err = "mirge_create: bad argument (max_read_len must be <= 128)";
+        return MIRGE_E_ARG;
+    }
+    mirge_ctx *ctx = new mirge_ctx();
+    *out = ctx;
+    ctx->device = device; ctx->S = n_samples; ctx->spike_in = spike_in ? 1 : 0;
+    ctx->W = max_read_len <= 64 ? 2 : 4;
+    ctx->max_len = ctx->W * 32;
+    ctx->max_unique = max_unique;
+    ctx->processed.assign(n_samples, 0);
+    memset(&ctx->tp, 0, sizeof ctx->tp);
+    ctx->tp.mode = 0; ctx->tp.error_rate = 0.12; ctx->tp.min_overlap = 3; ctx->tp.min_length = 16;
+    memset(ctx->prof_ms, 0, sizeof ctx->prof_ms); memset(ctx->prof_n, 0, sizeof ctx->prof_n);
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    u64 cap = 1024;
+    while (cap < 2 * max_unique) cap <<= 1;
+    ctx->table_cap = cap;
+    const size_t esz = ctx->W == 2 ? sizeof(TEntry<2>) : sizeof(TEntry<4>);
+    CK(cudaMalloc(&ctx->d_slots, cap * esz));
+    CK(cudaMalloc(&ctx->d_useq, max_unique * ctx->W * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_unmask, max_unique * (ctx->W / 2) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_ulen, max_unique));
+    CK(cudaMalloc(&ctx->d_counts, max_unique * (size_t)n_samples * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_round_of, max_unique));
+    CK(cudaMalloc(&ctx->d_mm_of, max_unique));
+    CK(cudaMalloc(&ctx->d_ref_of, max_unique * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_pos_of, max_unique * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_ctr, (2 + (size_t)n_samples) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_len_hist, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_todo[0], max_unique * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo[1], max_unique * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 1) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_round_stats, 2 * MIRGE_N_ROUNDS * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_lib_totals, (size_t)n_samples * MIRGE_N_TOTALS * sizeof(i64)));
+    CK(cudaMemsetAsync(ctx->d_slots, 0, cap * esz, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counts, 0, max_unique * (size_t)n_samples * sizeof(u32), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (2 + (size_t)n_samples) * sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MIRGE_OK;
+}
+
+static void free_lib(DevLib &l)
+{
+    cudaFree(l.seq); cudaFree(l.amb); cudaFree(l.ref_off);
+    for (int t = 0; t < l.ntabs; t++) { cudaFree(l.tab_off[t]); cudaFree(l.tab_pos[t]); }
+    l = DevLib();
+}
+
+void mirge_destroy(mirge_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (int i = 0; i < MIRGE_N_LIBS; i++) free_lib(ctx->libs[i]);
+    cudaFree(ctx->d_text); cudaFree(ctx->d_tile); cudaFree(ctx->d_scan); cudaFree(ctx->d_lines);
+    cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
+    cudaFree(ctx->d_slots); cudaFree(ctx->d_useq); cudaFree(ctx->d_unmask); cudaFree(ctx->d_ulen); cudaFree(ctx->d_counts);
+    cudaFree(ctx->d_round_of); cudaFree(ctx->d_mm_of); cudaFree(ctx->d_ref_of); cudaFree(ctx->d_pos_of);
+    cudaFree(ctx->d_ctr); cudaFree(ctx->d_len_hist); cudaFree(ctx->d_todo[0]); cudaFree(ctx->d_todo[1]);
+    cudaFree(ctx->d_todo_n); cudaFree(ctx->d_round_stats);
+    cudaFree(ctx->d_mir_quant); cudaFree(ctx->d_mir_iscan); cudaFree(ctx->d_lib_totals);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int mirge_set_stream(mirge_ctx *ctx, void *cuda_stream)
+{
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return MIRGE_OK;
+}
+
+int mirge_sync(mirge_ctx *ctx)
+{
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u64 flags = 0;
+    CK(cudaMemcpy(&flags, ctx->d_ctr + 1, sizeof(u64), cudaMemcpyDeviceToHost));
+    const u32 f = (u32)flags;
+    if (f & ERRF_FORMAT) return fail(ctx, MIRGE_E_FORMAT, "FASTQ format error: record does not start with '@'/'+' or sequence and quality lengths differ");
+    if (f & ERRF_TOOLONG) return fail(ctx, MIRGE_E_TOOLONG, "a read is longer than max_read_len");
+    if (f & ERRF_FULL) return fail(ctx, MIRGE_E_FULL, "unique-sequence table full: raise max_unique");
+    return MIRGE_OK;
+}
+
+int mirge_set_adapter(mirge_ctx *ctx, const char *spec, double error_rate, int min_overlap, int min_length, int qual_cutoff)
+{
+    if (!spec || min_length < 0 || min_length > 255) return fail(ctx, MIRGE_E_ARG, "mirge_set_adapter: bad argument");
+    TrimParams tp;
+    memset(&tp, 0, sizeof tp);
+    tp.error_rate = error_rate; tp.min_overlap = min_overlap; tp.min_length = min_length;
+    if (spec[0] == '+') {
+        tp.mode = 2; tp.uncond = atoi(spec);       // UnconditionalCutter(int(adapter)), trim_file.py:34-35
+    } else if (strcmp(spec, "none") == 0) {
+        tp.mode = 0;
+    } else {
+        tp.mode = 1;
+        const char *p = spec;
+        while (*p) {
+            const char *q = strchr(p, ',');
+            size_t n = q ? (size_t)(q - p) : strlen(p);
+            if (n == 0) return fail(ctx, MIRGE_E_ARG, "The adapter sequence is empty.");
+            if (isdigit((unsigned char)p[0])) return fail(ctx, MIRGE_E_ARG, "Adapter sequence starts with a digit.");
+            if (n > MIRGE_MAX_ADAPTER_LEN) return fail(ctx, MIRGE_E_ARG, "adapter longer than 64 nt is not supported");
+            if (tp.n_adapters == MIRGE_MAX_ADAPTERS) return fail(ctx, MIRGE_E_ARG, "more than 8 adapters are not supported");
+            const int a = tp.n_adapters++;
+            tp.alen[a] = (int)n;
+            for (size_t i = 0; i < n; i++) {
+                const int c = base_code((unsigned char)p[i]);
+                if (c > 3) return fail(ctx, MIRGE_E_ARG, "adapter must consist of A, C, G, T/U (wildcards and anchors are not supported)");
+                tp.aw[a][i >> 5] |= (u64)c << ((i & 31) * 2);
+                tp.peq[a][c] |= 1ull << i;
+            }
+            p += n;
+            if (*p == ',') p++;
+        }
+    }
+    ctx->tp = tp;
+    ctx->qual_cutoff = qual_cutoff;
+    return MIRGE_OK;
+}
+
+int mirge_detect_phred(const char *buf, uint64_t n)
+{
+    uint64_t p = 0; int line = 0;
+    while (p < n && line < 3) { if (buf[p] == '\n') line++; p++; }
+    for (; p < n && buf[p] != '\n'; p++) if ((unsigned char)buf[p] > 74) return 64;
+    return 33;
+}
+
+__global__ void k_set_u32(u32 *p, u32 v) { *p = v; }
+
+template <int W>
+static int feed_device_impl(mirge_ctx *ctx, int sample, const unsigned char *d_text, uint64_t nbytes, int phred_base, int last_char)
+{
+    cudaStream_t st = ctx->stream;
+    const u64 ntiles = (nbytes + K0_TILE_BYTES - 1) / K0_TILE_BYTES;
+    CK(ensure(&ctx->d_tile, &ctx->tile_cap, ntiles + 2));
+    CK(ensure(&ctx->d_scan, &ctx->scan_cap, scan_scratch_elems(ntiles + 1)));
+    const uint4 *t16 = reinterpret_cast<const uint4 *>(d_text);
+    { ProfScope ps(ctx, KID_K0_COUNT);
+      CK(cudaMemsetAsync(ctx->d_tile + ntiles, 0, sizeof(u32), st));
+      k0_count_newlines<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, nbytes, ctx->d_tile); }
+    { ProfScope ps(ctx, KID_K0_SCAN);
+      device_excl_scan(ctx->d_tile, ctx->d_tile, ntiles + 1, ctx->d_scan, st); }
+    u32 n_newlines = 0;
+    CK(cudaMemcpyAsync(&n_newlines, ctx->d_tile + ntiles, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const u64 n_lines = (u64)n_newlines + (last_char != '\n' ? 1 : 0);
+    if (n_lines % 4 != 0) return fail(ctx, MIRGE_E_FORMAT, "FASTQ chunk does not hold a whole number of 4-line records");
+    const u64 nrec = n_lines / 4;
+    CK(ensure(&ctx->d_lines, &ctx->lines_cap, n_lines + 2));
+    if (nrec > ctx->rec_cap) {
+        cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
+        ctx->d_bases = ctx->d_nmask = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
+        const size_t cap = nrec + nrec / 8 + 64;
+        CK(cudaMalloc(&ctx->d_bases, cap * W * sizeof(u64)));
+        CK(cudaMalloc(&ctx->d_nmask, cap * (W / 2) * sizeof(u64)));
+        CK(cudaMalloc(&ctx->d_meta, cap * sizeof(u32)));
+        ctx->rec_cap = cap;
+    }
+    { ProfScope ps(ctx, KID_K0_LINES);
+      CK(cudaMemsetAsync(ctx->d_lines, 0, sizeof(u32), st));
+      k0_line_starts<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, nbytes, ctx->d_tile, ctx->d_lines);
+      if (last_char != '\n') k_set_u32<<<1, 1, 0, st>>>(ctx->d_lines + n_lines, (u32)(nbytes + 1)); }
+    K0Params kp; kp.phred_base = phred_base; kp.qual_cutoff = ctx->qual_cutoff; kp.max_len = ctx->max_len;
+    { ProfScope ps(ctx, KID_K0_PACK);
+      k0_pack<W><<<grid_for(nrec, 256, 148 * 16), 256, 0, st>>>(d_text, ctx->d_lines, nrec, kp, ctx->d_bases, ctx->d_nmask,
+                                                               ctx->d_meta, (u32 *)(ctx->d_ctr + 1)); }
+    K1Counters kc; kc.kept = ctx->d_ctr + 2; kc.len_hist = ctx->d_len_hist;
+    { ProfScope ps(ctx, KID_K1_TRIM);
+      k1_trim_collapse<W><<<grid_for(nrec, 128, 148 * 16), 128, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample,
+                                                                        ctx->tp, table_view<W>(ctx), kc); }
+    CK(cudaGetLastError());
+    ctx->processed[sample] += nrec;
+    ctx->annotated = false; ctx->tallied = false;
+    return MIRGE_OK;
+}
+
+int mirge_feed_fastq_device(mirge_ctx *ctx, int sample, const void *fastq_dev, uint64_t nbytes, int phred_base)
+{
+    if (sample < 0 || sample >= ctx->S || nbytes >= 0xFFFFFFF0ull || ((uintptr_t)fastq_dev & 15)) return fail(ctx, MIRGE_E_ARG, "mirge_feed_fastq_device: bad argument (chunk must be < 4 GiB and 16-byte aligned)");
+    if (nbytes == 0) return MIRGE_OK;
+    CK(cudaSetDevice(ctx->device));
+    unsigned char last = 0;
+    CK(cudaMemcpyAsync(&last, (const unsigned char *)fastq_dev + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ctx->W == 2 ? feed_device_impl<2>(ctx, sample, (const unsigned char *)fastq_dev, nbytes, phred_base, last)
+                       : feed_device_impl<4>(ctx, sample, (const unsigned char *)fastq_dev, nbytes, phred_base, last);
+}
+
+int mirge_feed_fastq(mirge_ctx *ctx, int sample, const char *fastq, uint64_t nbytes, int phred_base)
+{
+    if (sample < 0 || sample >= ctx->S || !fastq || nbytes >= 0xFFFFFFF0ull) return fail(ctx, MIRGE_E_ARG, "mirge_feed_fastq: bad argument (chunk must be < 4 GiB)");
+    if (nbytes == 0) return MIRGE_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ensure(&ctx->d_text, &ctx->text_cap, (size_t)nbytes + 64));
+    { ProfScope ps(ctx, KID_H2D);
+      CK(cudaMemcpyAsync(ctx->d_text, fastq, nbytes, cudaMemcpyHostToDevice, ctx->stream)); }
+    const int last = (unsigned char)fastq[nbytes - 1];
+    return ctx->W == 2 ? feed_device_impl<2>(ctx, sample, ctx->d_text, nbytes, phred_base, last)
+                       : feed_device_impl<4>(ctx, sample, ctx->d_text, nbytes, phred_base, last);
+}
+
+int mirge_get_stats(mirge_ctx *ctx, uint64_t *processed, uint64_t *kept, uint64_t *n_unique)
+{
+    int rc = mirge_sync(ctx);
+    if (rc) return rc;
+    std::vector<u64> h(2 + ctx->S);
+    CK(cudaMemcpy(h.data(), ctx->d_ctr, h.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (n_unique) *n_unique = h[0] < ctx->max_unique ? h[0] : ctx->max_unique;
+    for (int s = 0; s < ctx->S; s++) {
+        if (processed) processed[s] = ctx->processed[s];
+        if (kept) kept[s] = h[2 + s];
+    }
+    return MIRGE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// libraries
+// ---------------------------------------------------------------------------
+int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_ascii, const uint64_t *offsets)
+{
+    if (lib_id < 0 || lib_id >= MIRGE_N_LIBS || lib_id == 8 || n_refs < 0 || (n_refs > 0 && (!seq_ascii || !offsets)))
+        return fail(ctx, MIRGE_E_ARG, "mirge_load_library: bad argument");
+    const u64 total = n_refs ? offsets[n_refs] : 0;
+    if (total >= 0xFFFFFF00ull) return fail(ctx, MIRGE_E_ARG, "library larger than 4 Gbases is not supported");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(cudaStreamSynchronize(st));
+    DevLib &l = ctx->libs[lib_id];
+    free_lib(l);
+    ProfScope ps(ctx, KID_LIB_BUILD);
+    l.n_refs = n_refs; l.total = (u32)total;
+    const size_t nw64 = (total + 63) / 64;
+    CK(cudaMalloc(&l.seq, (2 * nw64 + 8) * sizeof(u64)));
+    CK(cudaMalloc(&l.amb, (nw64 + 8) * sizeof(u64)));
+    CK(cudaMemsetAsync(l.seq, 0, (2 * nw64 + 8) * sizeof(u64), st));
+    CK(cudaMemsetAsync(l.amb, 0, (nw64 + 8) * sizeof(u64), st));
+    std::vector<u32> off32(n_refs + 1);
+    for (int i = 0; i <= n_refs; i++) off32[i] = (u32)(n_refs ? offsets[i] : 0);
+    CK(cudaMalloc(&l.ref_off, (size_t)(n_refs + 1) * sizeof(u32)));
+    CK(cudaMemcpyAsync(l.ref_off, off32.data(), (size_t)(n_refs + 1) * sizeof(u32), cudaMemcpyHostToDevice, st));
+    if (total == 0) { CK(cudaStreamSynchronize(st)); return MIRGE_OK; }
+    unsigned char *d_ascii = nullptr;
+    CK(cudaMalloc(&d_ascii, total));
+    CK(cudaMemcpyAsync(d_ascii, seq_ascii, total, cudaMemcpyHostToDevice, st));
+    k2_pack_library<<<(unsigned)((nw64 + 127) / 128), 128, 0, st>>>(d_ascii, (u32)total, l.seq, l.amb);
+    // seed tables: the miRNA library serves the 3-seed isomiR round on reads as
+    // short as 13 nt (k = 4..8); the big mRNA library gets a 12-mer table.
+    std::vector<int> ks;
+    if (lib_id == MIRGE_LIB_MIRNA) ks = {4, 5, 6, 7, 8};
+    else if (total > (8u << 20)) ks = {8, 12};
+    else ks = {8};
+    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.n_refs = n_refs; L.total = (u32)total;
+    for (int k : ks) {
+        if ((u64)k > total) continue;
+        const u64 nb = 1ull << (2 * k);
+        u32 *boff = nullptr, *cursor = nullptr, *pos = nullptr, *scratch = nullptr;
+        CK(cudaMalloc(&boff, (nb + 1) * sizeof(u32)));
+        CK(cudaMalloc(&cursor, (nb + 1) * sizeof(u32)));
+        CK(cudaMalloc(&pos, (total + 1) * sizeof(u32)));
+        CK(cudaMalloc(&scratch, scan_scratch_elems(nb + 1) * sizeof(u32)));
+        CK(cudaMemsetAsync(boff, 0, (nb + 1) * sizeof(u32), st));
+        const int grid = grid_for(total, 256, 148 * 8);
+        k2_kmer_pass<<<grid, 256, 0, st>>>(L, k, 0, boff, nullptr);
+        device_excl_scan(boff, boff, nb + 1, scratch, st);
+        CK(cudaMemcpyAsync(cursor, boff, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        k2_kmer_pass<<<grid, 256, 0, st>>>(L, k, 1, cursor, pos);
+        CK(cudaStreamSynchronize(st));
+        cudaFree(cursor); cudaFree(scratch);
+        const int t = l.ntabs++;
+        l.tab_k[t] = k; l.tab_off[t] = boff; l.tab_pos[t] = pos;
+    }
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_ascii);
+    CK(cudaGetLastError());
+    ctx->annotated = false; ctx->tallied = false;
+    return MIRGE_OK;
+}
+
+struct RoundSpec { int lib, len_filter, mode, param, trim5, trim3, highest, polyT; };
+// runAnnotationPipeline.py:574-599
+static const RoundSpec ROUNDS[MIRGE_N_ROUNDS] = {
+    {MIRGE_LIB_MIRNA, -26, 0, 0, 0, 0, 0, 0},        // bowtie mirna -n 0, len < 26
+    {MIRGE_LIB_HAIRPIN, 25, 0, 1, 0, 0, 0, 0},       // hairpin -n 1, len > 25
+    {MIRGE_LIB_MATURE_TRNA, 0, 1, 1, 0, 0, 1, 0},    // mature tRNA -v 1 -a --best --strata
+    {MIRGE_LIB_PRE_TRNA, 0, 1, 0, 0, 0, 1, 1},       // pre-tRNA poly-T round, -v 0 -a --best --strata
+    {MIRGE_LIB_SNORNA, 0, 0, 1, 0, 0, 0, 0},         // snoRNA -n 1
+    {MIRGE_LIB_RRNA, 0, 0, 1, 0, 0, 0, 0},           // rRNA -n 1
+    {MIRGE_LIB_NCRNA_OTHERS, 0, 0, 1, 0, 0, 0, 0},   // ncRNA others -n 1
+    {MIRGE_LIB_MRNA, 0, 0, 0, 0, 0, 0, 0},           // mRNA -n 0
+    {MIRGE_LIB_MIRNA, 0, 1, 2, 1, 2, 0, 0},          // mirna -5 1 -3 2 -v 2 --best (isomiR)
+    {MIRGE_LIB_SPIKEIN, 0, 0, 0, 0, 0, 0, 0},        // spike-in -n 0
+};
+
+template <int W>
+static int annotate_impl(mirge_ctx *ctx)
+{
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->d_round_of, 0, ctx->max_unique, st));
+    CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 1) * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), st));
+    K2Arrays A;
+    A.useq = ctx->d_useq; A.unmask = ctx->d_unmask; A.ulen = ctx->d_ulen;
+    A.round_of = ctx->d_round_of; A.ref_of = ctx->d_ref_of; A.pos_of = ctx->d_pos_of; A.mm_of = ctx->d_mm_of;
+    const int nrounds = ctx->spike_in ? 10 : 9;
+    for (int r = 0; r < nrounds; r++) {
+        const RoundSpec &rs = ROUNDS[r];
+        const DevLib &l = ctx->libs[rs.lib];
+        LibView L; L.seq = l.total ? l.seq : nullptr; L.amb = l.amb; L.ref_off = l.ref_off; L.n_refs = l.n_refs; L.total = l.total;
+        RoundParams R;
+        memset(&R, 0, sizeof R);
+        R.round = r; R.len_filter = rs.len_filter; R.mode = rs.mode; R.param = rs.param; R.trim5 = rs.trim5; R.trim3 = rs.trim3;
+        R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs;
+        for (int t = 0; t < l.ntabs; t++) { R.tabs[t].k = l.tab_k[t]; R.tabs[t].bucket_off = l.tab_off[t]; R.tabs[t].pos = l.tab_pos[t]; }
+        const u32 *todo_in = r == 0 ? nullptr : ctx->d_todo[(r - 1) & 1];
+        const u64 *n_in = r == 0 ? ctx->d_ctr : ctx->d_todo_n + r;
+        ProfScope ps(ctx, KID_K2_ROUND);
+        k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+                                            ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
+    }
+    CK(cudaGetLastError());
+    ctx->annotated = true; ctx->tallied = false;
+    return MIRGE_OK;
+}
+
+int mirge_annotate(mirge_ctx *ctx)
+{
+    CK(cudaSetDevice(ctx->device));
+    return ctx->W == 2 ? annotate_impl<2>(ctx) : annotate_impl<4>(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// tallies
+// ---------------------------------------------------------------------------
+int mirge_tally(mirge_ctx *ctx)
+{
+    if (!ctx->annotated) return fail(ctx, MIRGE_E_STATE, "mirge_tally called before mirge_annotate");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    u64 U = 0;
+    CK(cudaMemcpyAsync(&U, ctx->d_ctr, sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (U > ctx->max_unique) U = ctx->max_unique;
+    const int S = ctx->S, n_mir = ctx->libs[MIRGE_LIB_MIRNA].n_refs, n_seg = n_mir + MIRGE_N_TOTALS;
+    if (ctx->tally_nmir != n_mir) {
+        cudaFree(ctx->d_mir_quant); cudaFree(ctx->d_mir_iscan);
+        CK(cudaMalloc(&ctx->d_mir_quant, (size_t)(n_mir + 1) * S * sizeof(i64)));
+        CK(cudaMalloc(&ctx->d_mir_iscan, (size_t)(n_mir + 1) * S * sizeof(i64)));
+        ctx->tally_nmir = n_mir;
+    }
+    const u32 n_tiles = (u32)((U + RS_TILE - 1) / RS_TILE);
+    u32 *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr}, *hist = nullptr, *scratch = nullptr, *seg_start = nullptr, *seg_end = nullptr;
+    i64 *seg_q = nullptr, *seg_i = nullptr, *seg_u = nullptr;
+    const size_t hist_n = (size_t)256 * (n_tiles ? n_tiles : 1);
+    for (int b = 0; b < 2; b++) { CK(cudaMalloc(&keys[b], (U + 1) * sizeof(u32))); CK(cudaMalloc(&vals[b], (U + 1) * sizeof(u32))); }
+    CK(cudaMalloc(&hist, hist_n * sizeof(u32)));
+    CK(cudaMalloc(&scratch, scan_scratch_elems(hist_n) * sizeof(u32)));
+    CK(cudaMalloc(&seg_start, (size_t)n_seg * sizeof(u32)));
+    CK(cudaMalloc(&seg_end, (size_t)n_seg * sizeof(u32)));
+    CK(cudaMalloc(&seg_q, (size_t)n_seg * S * sizeof(i64)));
+    CK(cudaMalloc(&seg_i, (size_t)n_seg * S * sizeof(i64)));
+    CK(cudaMalloc(&seg_u, (size_t)n_seg * S * sizeof(i64)));
+    CK(cudaMemsetAsync(seg_start, 0, (size_t)n_seg * sizeof(u32), st));
+    CK(cudaMemsetAsync(seg_end, 0, (size_t)n_seg * sizeof(u32), st));
+    const int g = grid_for(U, 256, 148 * 8);
+    { ProfScope ps(ctx, KID_K3_KEYS);
+      k3_make_keys<<<g, 256, 0, st>>>(ctx->d_round_of, ctx->d_ref_of, ctx->d_ctr, n_mir, keys[0], vals[0]); }
+    int bits = 1;
+    while ((1 << bits) < n_seg) bits++;
+    int cur = 0;
+    if (n_tiles) {
+        ProfScope ps(ctx, KID_K3_SORT);
+        const int gt = (int)(n_tiles < 148u * 8u ? n_tiles : 148u * 8u);
+        for (int shift = 0; shift < bits; shift += 8) {
+            k3_rs_hist<<<gt, RS_THREADS, 0, st>>>(keys[cur], ctx->d_ctr, shift, n_tiles, hist);
+            device_excl_scan(hist, hist, hist_n, scratch, st);
+            k3_rs_scatter<<<gt, RS_THREADS, 0, st>>>(keys[cur], vals[cur], ctx->d_ctr, shift, n_tiles, hist, keys[cur ^ 1], vals[cur ^ 1]);
+            cur ^= 1;
+        }
+    }
+    { ProfScope ps(ctx, KID_K3_BOUNDS);
+      k3_seg_bounds<<<g, 256, 0, st>>>(keys[cur], ctx->d_ctr, seg_start, seg_end); }
+    { ProfScope ps(ctx, KID_K3_REDUCE);
+      k3_seg_reduce<<<grid_for((u64)n_seg * 32, 256, 148 * 8), 256, 0, st>>>(vals[cur], seg_start, seg_end, n_seg, ctx->d_counts,
+                                                                            ctx->d_round_of, S, seg_q, seg_i, seg_u); }
+    { ProfScope ps(ctx, KID_K3_FINAL);
+      k3_finalize<<<(S + 63) / 64, 64, 0, st>>>(seg_q, seg_i, seg_u, n_mir, S, ctx->d_mir_quant, ctx->d_mir_iscan, ctx->d_lib_totals); }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    for (int b = 0; b < 2; b++) { cudaFree(keys[b]); cudaFree(vals[b]); }
+    cudaFree(hist); cudaFree(scratch); cudaFree(seg_start); cudaFree(seg_end); cudaFree(seg_q); cudaFree(seg_i); cudaFree(seg_u);
+    ctx->tallied = true;
+    return MIRGE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// export
+// ---------------------------------------------------------------------------
+int mirge_export_unique(mirge_ctx *ctx, uint64_t cap, int stride, char *seq, uint8_t *len, uint32_t *counts,
+                        int8_t *round_of, int32_t *ref_of, int32_t *pos_of, int8_t *mm_of)
+{
+    u64 U = 0;
+    int rc = mirge_get_stats(ctx, nullptr, nullptr, (uint64_t *)&U);
+    if (rc) return rc;
+    if (cap < U) return fail(ctx, MIRGE_E_ARG, "mirge_export_unique: capacity smaller than n_unique");
+    if (seq && stride < ctx->max_len) return fail(ctx, MIRGE_E_ARG, "mirge_export_unique: stride smaller than max_read_len");
+    const int W = ctx->W;
+    std::vector<u8> hl(U);
+    CK(cudaMemcpy(hl.data(), ctx->d_ulen, U, cudaMemcpyDeviceToHost));
+    if (len) memcpy(len, hl.data(), U);
+    if (seq) {
+        std::vector<u64> hs(U * W), hn(U * (W / 2));
+        CK(cudaMemcpy(hs.data(), ctx->d_useq, U * W * sizeof(u64), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hn.data(), ctx->d_unmask, U * (W / 2) * sizeof(u64), cudaMemcpyDeviceToHost));
+        static const char ACGT[4] = {'A', 'C', 'G', 'T'};
+        for (u64 u = 0; u < U; u++) {
+            char *o = seq + u * (u64)stride;
+            const int n = hl[u];
+            for (int i = 0; i < n; i++) {
+                const int isn = (int)((hn[u * (W / 2) + (i >> 6)] >> (i & 63)) & 1);
+                o[i] = isn ? 'N' : ACGT[(hs[u * W + (i >> 5)] >> ((i & 31) * 2)) & 3];
+            }
+            if (n < stride) memset(o + n, 0, (size_t)(stride - n));
+        }
+    }
+    if (counts) CK(cudaMemcpy(counts, ctx->d_counts, U * ctx->S * sizeof(u32), cudaMemcpyDeviceToHost));
+    if (ctx->annotated) {
+        if (round_of) CK(cudaMemcpy(round_of, ctx->d_round_of, U, cudaMemcpyDeviceToHost));
+        if (ref_of) CK(cudaMemcpy(ref_of, ctx->d_ref_of, U * sizeof(int), cudaMemcpyDeviceToHost));
+        if (pos_of) CK(cudaMemcpy(pos_of, ctx->d_pos_of, U * sizeof(int), cudaMemcpyDeviceToHost));
+        if (mm_of) CK(cudaMemcpy(mm_of, ctx->d_mm_of, U, cudaMemcpyDeviceToHost));
+    } else {
+        if (round_of) memset(round_of, 0, U);
+    }
+    return MIRGE_OK;
+}
+
+int mirge_export_tables(mirge_ctx *ctx, int64_t *mir_quant, int64_t *mir_iscan, int64_t *lib_totals, uint64_t *len_hist,
+                        uint64_t *round_processed, uint64_t *round_aligned)
+{
+    int rc = mirge_sync(ctx);
+    if (rc) return rc;
+    const int S = ctx->S;
+    if ((mir_quant || mir_iscan || lib_totals) && !ctx->tallied) return fail(ctx, MIRGE_E_STATE, "mirge_export_tables called before mirge_tally");
+    const size_t nm = (size_t)ctx->libs[MIRGE_LIB_MIRNA].n_refs;
+    if (mir_quant && nm) CK(cudaMemcpy(mir_quant, ctx->d_mir_quant, nm * S * sizeof(i64), cudaMemcpyDeviceToHost));
+    if (mir_iscan && nm) CK(cudaMemcpy(mir_iscan, ctx->d_mir_iscan, nm * S * sizeof(i64), cudaMemcpyDeviceToHost));
+    if (lib_totals) CK(cudaMemcpy(lib_totals, ctx->d_lib_totals, (size_t)S * MIRGE_N_TOTALS * sizeof(i64), cudaMemcpyDeviceToHost));
+    if (len_hist) CK(cudaMemcpy(len_hist, ctx->d_len_hist, (size_t)(ctx->max_len + 1) * S * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (round_processed) CK(cudaMemcpy(round_processed, ctx->d_round_stats, MIRGE_N_ROUNDS * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (round_aligned) CK(cudaMemcpy(round_aligned, ctx->d_round_stats + MIRGE_N_ROUNDS, MIRGE_N_ROUNDS * sizeof(u64), cudaMemcpyDeviceToHost));
+    return MIRGE_OK;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU exchange
+// ---------------------------------------------------------------------------
+int mirge_record_bytes(const mirge_ctx *ctx)
+{
+    const int b = 8 * (ctx->W + ctx->W / 2) + 4 * (1 + ctx->S);
+    return (b + 7) & ~7;
+}
+
+__global__ void k_excl_scan_small(const u64 *in, u64 *out, int n)
+{
+    u64 acc = 0;
+    for (int i = 0; i < n; i++) { out[i] = acc; acc += in[i]; }
+}
+
+int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint64_t cap_records, uint64_t *part_counts)
+{
+    if (n_parts < 1 || n_parts > 1024 || !part_counts) return fail(ctx, MIRGE_E_ARG, "mirge_export_records_device: bad argument");
+    u64 U = 0;
+    int rc = mirge_get_stats(ctx, nullptr, nullptr, (uint64_t *)&U);
+    if (rc) return rc;
+    if (cap_records < U) return fail(ctx, MIRGE_E_ARG, "mirge_export_records_device: buffer too small");
+    cudaStream_t st = ctx->stream;
+    u64 *d_cnt = nullptr;
+    CK(cudaMalloc(&d_cnt, 2 * (size_t)n_parts * sizeof(u64)));
+    CK(cudaMemsetAsync(d_cnt, 0, 2 * (size_t)n_parts * sizeof(u64), st));
+    const int rb = mirge_record_bytes(ctx), g = grid_for(U, 128, 148 * 8);
+    {
+        ProfScope ps(ctx, KID_EXCHANGE);
+        if (ctx->W == 2) {
+            k1_export_records<2><<<g, 128, 0, st>>>(table_view<2>(ctx), U, n_parts, rb, 1, d_cnt, nullptr, nullptr);
+            k_excl_scan_small<<<1, 1, 0, st>>>(d_cnt, d_cnt + n_parts, n_parts);
+            k1_export_records<2><<<g, 128, 0, st>>>(table_view<2>(ctx), U, n_parts, rb, 0, d_cnt, d_cnt + n_parts, (unsigned char *)dev_buf);
+        } else {
+            k1_export_records<4><<<g, 128, 0, st>>>(table_view<4>(ctx), U, n_parts, rb, 1, d_cnt, nullptr, nullptr);
+            k_excl_scan_small<<<1, 1, 0, st>>>(d_cnt, d_cnt + n_parts, n_parts);
+            k1_export_records<4><<<g, 128, 0, st>>>(table_view<4>(ctx), U, n_parts, rb, 0, d_cnt, d_cnt + n_parts, (unsigned char *)dev_buf);
+        }
+    }
+    CK(cudaMemcpyAsync(part_counts, d_cnt, (size_t)n_parts * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_cnt);
+    CK(cudaGetLastError());
+    return MIRGE_OK;
+}
+
+int mirge_reset_unique(mirge_ctx *ctx)
+{
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t esz = ctx->W == 2 ? sizeof(TEntry<2>) : sizeof(TEntry<4>);
+    CK(cudaMemsetAsync(ctx->d_slots, 0, ctx->table_cap * esz, st));
+    CK(cudaMemsetAsync(ctx->d_counts, 0, ctx->max_unique * (size_t)ctx->S * sizeof(u32), st));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(u64), st));
+    ctx->annotated = false; ctx->tallied = false;
+    return MIRGE_OK;
+}
+
+int mirge_import_records_device(mirge_ctx *ctx, const void *dev_buf, uint64_t n_records)
+{
+    if (n_records == 0) return MIRGE_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int rb = mirge_record_bytes(ctx), g = grid_for(n_records, 128, 148 * 8);
+    ProfScope ps(ctx, KID_EXCHANGE);
+    if (ctx->W == 2) k1_import_records<2><<<g, 128, 0, ctx->stream>>>((const unsigned char *)dev_buf, n_records, rb, table_view<2>(ctx));
+    else k1_import_records<4><<<g, 128, 0, ctx->stream>>>((const unsigned char *)dev_buf, n_records, rb, table_view<4>(ctx));
+    CK(cudaGetLastError());
+    ctx->annotated = false; ctx->tallied = false;
+    return MIRGE_OK;
+}
+
+uint64_t mirge_hash_sequence(const char *seq, int len)
+{
+    u64 s[4] = {0, 0, 0, 0}, nm[2] = {0, 0};
+    if (len > 128) len = 128;
+    for (int i = 0; i < len; i++) {
+        int c = base_code((unsigned char)seq[i]);
+        if (c > 3) { nm[i >> 6] |= 1ull << (i & 63); c = 0; }
+        s[i >> 5] |= (u64)c << ((i & 31) * 2);
+    }
+    return owner_hash(key_hash_words(s, 4, nm, len));
+}
+
+// ---------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------
+int mirge_profile_enable(mirge_ctx *ctx, int on)
+{
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    ctx->spans.clear();
+    memset(ctx->prof_ms, 0, sizeof ctx->prof_ms); memset(ctx->prof_n, 0, sizeof ctx->prof_n);
+    ctx->prof = on != 0;
+    return MIRGE_OK;
+}
+
+int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const char **names)
+{
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &s : ctx->spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { ctx->prof_ms[s.kid] += t; ctx->prof_n[s.kid]++; }
+        cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+    }
+    ctx->spans.clear();
+    for (int k = 0; k < MIRGE_N_KERNELS; k++) {
+        if (ms) ms[k] = ctx->prof_ms[k];
+        if (launches) launches[k] = ctx->prof_n[k];
+        if (names) names[k] = KERNEL_NAMES[k];
+    }
+    return MIRGE_OK;
+}
+

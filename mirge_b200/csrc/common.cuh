@@ -1,0 +1,170 @@
+// common.cuh -- shared device helpers: 2-bit packed sequences, hashing, scans.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+typedef unsigned char u8;
+typedef long long i64;
+
+#define MIRGE_MAX_ADAPTERS 8
+#define MIRGE_MAX_ADAPTER_LEN 64
+
+// device error flags (DevCounters::err)
+#define ERRF_FORMAT 1u
+#define ERRF_TOOLONG 2u
+#define ERRF_FULL 4u
+
+// ---------------------------------------------------------------------------
+// Packed sequence: base i lives in bits [2i, 2i+1] of word i/32; A=0 C=1 G=2 T=3.
+// Ambiguity mask: bit i of word i/64 set when base i is not ACGT (packed as 0).
+// W = number of 64-bit base words (2 => <=64 nt, 4 => <=128 nt); NW = W/2.
+// ---------------------------------------------------------------------------
+template <int W>
+struct PSeq {
+    u64 s[W];
+    u64 nm[W / 2];
+};
+
+__host__ __device__ __forceinline__ int base_code(unsigned char c)
+{
+    c &= 0xDF;  // upper-case
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : (c == 'T' || c == 'U') ? 3 : 4;
+}
+
+template <int W>
+__device__ __forceinline__ int pseq_base(const PSeq<W> &p, int j)
+{
+    u64 w = p.s[0];
+#pragma unroll
+    for (int a = 1; a < W; a++) if ((j >> 5) == a) w = p.s[a];
+    return (int)((w >> ((j & 31) * 2)) & 3ull);
+}
+template <int W>
+__device__ __forceinline__ int pseq_isn(const PSeq<W> &p, int j)
+{
+    u64 w = p.nm[0];
+#pragma unroll
+    for (int a = 1; a < W / 2; a++) if ((j >> 6) == a) w = p.nm[a];
+    return (int)((w >> (j & 63)) & 1ull);
+}
+
+// keep bases [0, n): clear everything at and above base n
+template <int W>
+__device__ __forceinline__ void pseq_truncate(PSeq<W> &p, int n)
+{
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        int lo = w * 32;
+        if (n <= lo) p.s[w] = 0;
+        else if (n < lo + 32) p.s[w] &= (1ull << ((n - lo) * 2)) - 1ull;
+    }
+#pragma unroll
+    for (int w = 0; w < W / 2; w++) {
+        int lo = w * 64;
+        if (n <= lo) p.nm[w] = 0;
+        else if (n < lo + 64) p.nm[w] &= (1ull << (n - lo)) - 1ull;
+    }
+}
+
+// drop the first b bases (b >= 0).  Word selection is written as unrolled
+// compare-selects so the arrays stay in registers (no runtime indexing).
+template <int W>
+__device__ __forceinline__ void pseq_shift(PSeq<W> &p, int b)
+{
+    if (b <= 0) return;
+    {
+        int ws = b >> 5, bs = (b & 31) * 2;
+        u64 t[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            u64 lo = 0ull, hi = 0ull;
+#pragma unroll
+            for (int a = 0; a < W; a++) {
+                if (a == w + ws) lo = p.s[a];
+                if (a == w + ws + 1) hi = p.s[a];
+            }
+            t[w] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) p.s[w] = t[w];
+    }
+    {
+        const int NW = W / 2;
+        int ws = b >> 6, bs = b & 63;
+        u64 t[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            u64 lo = 0ull, hi = 0ull;
+#pragma unroll
+            for (int a = 0; a < NW; a++) {
+                if (a == w + ws) lo = p.nm[a];
+                if (a == w + ws + 1) hi = p.nm[a];
+            }
+            t[w] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+        }
+#pragma unroll
+        for (int w = 0; w < NW; w++) p.nm[w] = t[w];
+    }
+}
+
+// 64-bit hash of (packed key, ambiguity mask, length); identical on host and device.
+__host__ __device__ __forceinline__ u64 mix64(u64 x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+// Hash over a canonical 4+2 word form so that W=2 and W=4 contexts (and the
+// host) agree on the owner of a sequence.
+__host__ __device__ __forceinline__ u64 key_hash_words(const u64 *s, int W, const u64 *nm, int len)
+{
+    u64 h = 0x9E3779B97F4A7C15ULL ^ (u64)len;
+    for (int w = 0; w < 4; w++) h = mix64(h ^ (w < W ? s[w] : 0ull)) + 0x632BE59BD9B4E019ULL * (u64)(w + 1);
+    for (int w = 0; w < 2; w++) h = mix64(h ^ (w < W / 2 ? nm[w] : 0ull)) + 0xD6E8FEB86659FD93ULL * (u64)(w + 1);
+    return mix64(h);
+}
+// Owner rank of a key in the multi-GPU exchange = owner_hash(h) % n_ranks; re-mixed so
+// it is independent of the slot bits (low) and the fingerprint bits (high) of h.
+__host__ __device__ __forceinline__ u64 owner_hash(u64 h) { return mix64(h ^ 0xA5A5F00DDEADBEEFULL); }
+template <int W>
+__device__ __forceinline__ u64 pseq_hash(const PSeq<W> &p, int len)
+{
+    return key_hash_words(p.s, W, p.nm, len);
+}
+
+// ---------------------------------------------------------------------------
+// block-wide exclusive scan of one u32 per thread (blockDim.x multiple of 32, <= 1024)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 warp_incl_scan(u32 v)
+{
+    unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v += t;
+    }
+    return v;
+}
+// returns exclusive prefix; *total = block sum.  sh must hold 33 u32.
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *sh, u32 *total)
+{
+    unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    u32 inc = warp_incl_scan(v);
+    if (lane == 31) sh[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        u32 x = (lane < nw) ? sh[lane] : 0;
+        u32 xi = warp_incl_scan(x);
+        sh[lane] = xi - x;
+        if (lane == 31) sh[32] = xi;
+    }
+    __syncthreads();
+    u32 r = inc - v + sh[wid];
+    *total = sh[32];
+    __syncthreads();
+    return r;
+}

@@ -1,0 +1,328 @@
+// k1_trim.cuh -- K1: 3' adapter trim + length filter + collapse, one pass.
+//
+// Replaces, per read, the Worker.run modifier chain of utils/trim_file.py:52-55
+// (cutadapt AdapterCutter / UnconditionalCutter + min_length) and the dict
+// upsert of utils/quantReads.py:9-21.  Input is the packed record stream K0
+// wrote (bases via one 128-bit load per read at W=2, ambiguity mask, trim
+// window); output is the device hash table of unique sequences with per-sample
+// counts, the read-length histogram and the kept counter.
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// unique-sequence table: open addressing, linear probing, key stored inline.
+// tag = fp23 << 9 | len << 1 | ready ; 0 = empty.
+// ---------------------------------------------------------------------------
+template <int W> struct TEntry;
+template <> struct alignas(32) TEntry<2> { u64 s[2]; u64 nm[1]; u32 tag; u32 id; };
+template <> struct alignas(64) TEntry<4> { u64 s[4]; u64 nm[2]; u32 tag; u32 id; u64 pad; };
+
+template <int W>
+struct TableView {
+    TEntry<W> *slots;
+    u64 mask;            // capacity - 1 (capacity is a power of two)
+    u64 *useq;           // dense copies by unique id: [max_unique][W]
+    u64 *unmask;         // [max_unique][W/2]
+    u8 *ulen;            // [max_unique]
+    u32 *counts;         // [max_unique][S]
+    u64 max_unique;
+    u64 *n_unique;       // device counter
+    u32 *err;            // device error flags
+    int S;
+};
+
+// Table slots are written and read concurrently by different SMs.  Publication
+// follows the PTX memory model's release/acquire pattern: the inserting thread
+// writes the key, then st.release.gpu's the tag; probing threads ld.acquire.gpu
+// the tag and read the key with strong (relaxed.gpu) loads, so a READY tag
+// implies the key words are visible.
+__device__ __forceinline__ void ldcg_u64x2(const void *p, u64 &a, u64 &b)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ u64 ldcg_u64(const void *p)
+{
+    u64 a;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+__device__ __forceinline__ u32 ld_acquire_u32(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(u32 *p, u32 v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+template <int W>
+__device__ __forceinline__ bool entry_key_equal(const TEntry<W> *e, const PSeq<W> &k)
+{
+    bool eq = true;
+#pragma unroll
+    for (int w = 0; w < W; w += 2) {
+        u64 a, b;
+        ldcg_u64x2(&e->s[w], a, b);
+        eq = eq && (a == k.s[w]) && (b == k.s[w + 1]);
+    }
+#pragma unroll
+    for (int w = 0; w < W / 2; w++) eq = eq && (ldcg_u64(&e->nm[w]) == k.nm[w]);
+    return eq;
+}
+
+// Find or insert `key` (already truncated to len bases); returns its dense id,
+// or 0xFFFFFFFF when the table or the id space is exhausted (err flag set).
+template <int W>
+__device__ u32 table_upsert(const TableView<W> &T, const PSeq<W> &key, int len, u64 h)
+{
+    const u32 want = (((((u32)(h >> 41)) & 0x7FFFFFu) | 1u) << 9) | ((u32)len << 1);   // busy form (ready bit clear)
+    u64 slot = h & T.mask;
+    for (u64 probe = 0; probe <= T.mask; probe++) {
+        TEntry<W> *e = T.slots + slot;
+        u32 *tagp = &e->tag;
+        u32 t = ld_acquire_u32(tagp);
+        if (t == 0) {
+            u32 old = atomicCAS(tagp, 0u, want);
+            if (old == 0) {
+                u64 id = atomicAdd(T.n_unique, 1ull);
+                u32 id32 = 0xFFFFFFFFu;
+                if (id < T.max_unique) {
+                    id32 = (u32)id;
+#pragma unroll
+                    for (int w = 0; w < W; w++) T.useq[id * W + w] = key.s[w];
+#pragma unroll
+                    for (int w = 0; w < W / 2; w++) T.unmask[id * (W / 2) + w] = key.nm[w];
+                    T.ulen[id] = (u8)len;
+                } else {
+                    atomicOr(T.err, ERRF_FULL);
+                }
+#pragma unroll
+                for (int w = 0; w < W; w++) e->s[w] = key.s[w];
+#pragma unroll
+                for (int w = 0; w < W / 2; w++) e->nm[w] = key.nm[w];
+                e->id = id32;
+                st_release_u32(tagp, want | 1u);      // publish
+                return id32;
+            }
+            t = old;
+        }
+        if ((t | 1u) == (want | 1u)) {
+            while (!(t & 1u)) t = ld_acquire_u32(tagp);   // another thread is publishing this slot
+            if (entry_key_equal<W>(e, key)) {
+                u32 id;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(id) : "l"(&e->id) : "memory");
+                return id;
+            }
+        }
+        slot = (slot + 1) & T.mask;
+    }
+    atomicOr(T.err, ERRF_FULL);
+    return 0xFFFFFFFFu;
+}
+
+// ---------------------------------------------------------------------------
+// adapter matching
+// ---------------------------------------------------------------------------
+struct TrimParams {
+    int mode;            // 0 none, 1 3' adapters, 2 unconditional cut (+N)
+    int n_adapters;
+    int uncond;
+    int min_overlap;
+    int min_length;
+    int pad_;
+    double error_rate;
+    int alen[MIRGE_MAX_ADAPTERS];
+    u64 aw[MIRGE_MAX_ADAPTERS][2];     // packed adapter bases
+    u64 peq[MIRGE_MAX_ADAPTERS][4];    // bit i set iff adapter[i] == base
+};
+
+// cutadapt _align.pyx Aligner.locate for a BACK adapter, cell for cell
+// (see oracle/mirge_oracle.c:orc_locate).  Column entries are packed as
+// cost | matches << 8 | origin << 16.
+template <int W>
+__device__ bool locate_back(const PSeq<W> &p, int n, const u64 *aw, int m, double rate, int min_overlap,
+                            int &rstart, int &matches_out)
+{
+    u32 col[MIRGE_MAX_ADAPTER_LEN + 1];
+    const int k = (int)(rate * m);
+    for (int i = 0; i <= m; i++) col[i] = (u32)i;
+    int best_cost = m + n, best_matches = 0, best_origin = 0;
+    int last = m < k + 1 ? m : k + 1;
+    for (int j = 1; j <= n; j++) {
+        const int cj = pseq_isn<W>(p, j - 1) ? 4 : pseq_base<W>(p, j - 1);
+        u32 tmp = col[0];
+        u32 prev_new = (u32)j << 16;
+        col[0] = prev_new;
+        for (int i = 1; i <= last; i++) {
+            const int ai = (int)((aw[(i - 1) >> 5] >> (((i - 1) & 31) * 2)) & 3ull);
+            const u32 cur = col[i];
+            u32 e;
+            if (ai == cj) {
+                e = tmp + (1u << 8);
+            } else {
+                const u32 cd = (tmp & 0xFF) + 1, cdel = (cur & 0xFF) + 1, cins = (prev_new & 0xFF) + 1;
+                if (cd <= cdel && cd <= cins) e = tmp + 1;
+                else if (cins <= cdel) e = prev_new + 1;
+                else e = cur + 1;
+            }
+            tmp = cur;
+            col[i] = e;
+            prev_new = e;
+        }
+        while (last >= 0 && (int)(col[last] & 0xFF) > k) last--;
+        if (last < m) {
+            last++;
+        } else {
+            const u32 e = col[m];
+            const int cost = e & 0xFF, matches = (e >> 8) & 0xFF;
+            if (m >= min_overlap && (double)cost <= (double)m * rate &&
+                (matches > best_matches || (matches == best_matches && cost < best_cost))) {
+                best_matches = matches; best_cost = cost; best_origin = (int)(e >> 16);
+                if (cost == 0 && matches == m) break;
+            }
+        }
+    }
+    for (int i = m; i >= 0; i--) {
+        const u32 e = col[i];
+        const int cost = e & 0xFF, matches = (e >> 8) & 0xFF;
+        if (i >= min_overlap && (double)cost <= (double)i * rate &&
+            (matches > best_matches || (matches == best_matches && cost < best_cost))) {
+            best_matches = matches; best_cost = cost; best_origin = (int)(e >> 16);
+        }
+    }
+    if (best_cost == m + n) return false;
+    rstart = best_origin; matches_out = best_matches;
+    return true;
+}
+
+// Adapter.match_to (cutadapt adapters.py), where = BACK, no wildcards:
+// leftmost exact occurrence (str.find) first, else Aligner.locate.
+template <int W>
+__device__ __forceinline__ bool match_back(const PSeq<W> &p, int n, const TrimParams &tp, int a,
+                                           int &rstart, int &matches)
+{
+    const int m = tp.alen[a];
+    if (m <= n) {
+        u64 D = 0;
+        const u64 top = 1ull << (m - 1);
+        for (int j = 0; j < n; j++) {
+            const u64 pe = pseq_isn<W>(p, j) ? 0ull : tp.peq[a][pseq_base<W>(p, j)];
+            D = ((D << 1) | 1ull) & pe;
+            if (D & top) { rstart = j - m + 1; matches = m; return true; }
+        }
+    }
+    return locate_back<W>(p, n, tp.aw[a], m, tp.error_rate, tp.min_overlap, rstart, matches);
+}
+
+struct K1Counters {
+    u64 *kept;        // [S]
+    u64 *len_hist;    // [(max_len + 1)][S]
+};
+
+template <int W>
+__global__ void __launch_bounds__(128)
+k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
+                 u64 n_records, int sample, TrimParams tp, TableView<W> T, K1Counters ctr)
+{
+    const int NW = W / 2;
+    for (u64 r0 = (u64)blockIdx.x * blockDim.x; r0 < n_records; r0 += (u64)gridDim.x * blockDim.x) {
+        const u64 r = r0 + threadIdx.x;
+        bool kept = false;
+        int n = 0;
+        PSeq<W> p;
+        if (r < n_records) {
+            if (W == 2) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(bases) + r);
+                p.s[0] = v.x; p.s[1] = v.y;
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; w++) p.s[w] = __ldg(bases + r * W + w);
+            }
+#pragma unroll
+            for (int w = 0; w < NW; w++) p.nm[w] = __ldg(nmask + r * NW + w);
+            const u32 mt = __ldg(meta + r);
+            const int qstart = (mt >> 8) & 0xFF, qstop = (mt >> 16) & 0xFF;
+            n = qstop - qstart;
+            pseq_shift<W>(p, qstart);
+            pseq_truncate<W>(p, n);
+            if (tp.mode == 2) {
+                const int L = tp.uncond;
+                if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); n -= cut; }
+                else if (L < 0) { const int cut = (-L) < n ? (-L) : n; n -= cut; pseq_truncate<W>(p, n); }
+            } else if (tp.mode == 1) {
+                int best_rstart = -1, best_matches = -1;
+                for (int a = 0; a < tp.n_adapters; a++) {
+                    int rs, mt2;
+                    if (match_back<W>(p, n, tp, a, rs, mt2) && (best_rstart < 0 || mt2 > best_matches)) {
+                        best_rstart = rs; best_matches = mt2;
+                    }
+                }
+                if (best_rstart >= 0) { n = best_rstart; pseq_truncate<W>(p, n); }
+            }
+            kept = n >= tp.min_length;
+        }
+        if (kept) {
+            const u64 h = pseq_hash<W>(p, n);
+            const u32 id = table_upsert<W>(T, p, n, h);
+            if (id != 0xFFFFFFFFu) atomicAdd(&T.counts[(u64)id * T.S + sample], 1u);
+            atomicAdd(&ctr.len_hist[(u64)n * T.S + sample], 1ull);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, kept);
+        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&ctr.kept[sample], (u64)__popc(bal));
+    }
+}
+
+// Insert exchange records (multi-GPU): record = W + W/2 u64 words, then
+// u32 len, then S u32 counts, padded to 8 bytes.
+template <int W>
+__global__ void __launch_bounds__(128)
+k1_import_records(const unsigned char *__restrict__ buf, u64 n_records, int rec_bytes, TableView<W> T)
+{
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_records; r += (u64)gridDim.x * blockDim.x) {
+        const u64 *q = reinterpret_cast<const u64 *>(buf + r * (u64)rec_bytes);
+        PSeq<W> p;
+#pragma unroll
+        for (int w = 0; w < W; w++) p.s[w] = q[w];
+#pragma unroll
+        for (int w = 0; w < W / 2; w++) p.nm[w] = q[W + w];
+        const u32 *c = reinterpret_cast<const u32 *>(q + W + W / 2);
+        const int len = (int)c[0];
+        const u64 h = pseq_hash<W>(p, len);
+        const u32 id = table_upsert<W>(T, p, len, h);
+        if (id != 0xFFFFFFFFu)
+            for (int s = 0; s < T.S; s++) if (c[1 + s]) atomicAdd(&T.counts[(u64)id * T.S + s], c[1 + s]);
+    }
+}
+
+// Write every unique as an exchange record, grouped by owner = hash % n_parts.
+// Pass 1 (count_only) fills part_counts; after an exclusive scan into
+// part_cursor, pass 2 scatters.
+template <int W>
+__global__ void __launch_bounds__(128)
+k1_export_records(TableView<W> T, u64 n_unique, int n_parts, int rec_bytes, int count_only,
+                  u64 *__restrict__ part_counts, u64 *__restrict__ part_cursor, unsigned char *__restrict__ out)
+{
+    for (u64 id = (u64)blockIdx.x * blockDim.x + threadIdx.x; id < n_unique; id += (u64)gridDim.x * blockDim.x) {
+        u64 s[W], nm[W / 2];
+#pragma unroll
+        for (int w = 0; w < W; w++) s[w] = T.useq[id * W + w];
+#pragma unroll
+        for (int w = 0; w < W / 2; w++) nm[w] = T.unmask[id * (W / 2) + w];
+        const int len = T.ulen[id];
+        const u64 h = key_hash_words(s, W, nm, len);
+        const int part = (int)(owner_hash(h) % (u64)n_parts);
+        if (count_only) { atomicAdd(&part_counts[part], 1ull); continue; }
+        const u64 dst = atomicAdd(&part_cursor[part], 1ull);
+        u64 *q = reinterpret_cast<u64 *>(out + dst * (u64)rec_bytes);
+#pragma unroll
+        for (int w = 0; w < W; w++) q[w] = s[w];
+#pragma unroll
+        for (int w = 0; w < W / 2; w++) q[W + w] = nm[w];
+        u32 *c = reinterpret_cast<u32 *>(q + W + W / 2);
+        c[0] = (u32)len;
+        for (int x = 0; x < T.S; x++) c[1 + x] = T.counts[id * T.S + x];
+        if (((1 + T.S) & 1)) c[1 + T.S] = 0;
+    }
+}
