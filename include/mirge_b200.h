@@ -57,6 +57,10 @@ int mirge_set_stream(mirge_ctx *ctx, void *cuda_stream);
 /* Wait for queued work and surface device-side error flags. */
 int mirge_sync(mirge_ctx *ctx);
 
+/* Return to the freshly created state (libraries, adapter and stream are
+ * kept): what starting a new `miRge2.0 annotate` run does to the four dicts. */
+int mirge_reset(mirge_ctx *ctx);
+
 /* -- stage 1: trim + quality/length filter + collapse ------------------- */
 
 /* Worker.__init__ (utils/trim_file.py:24-41): spec is the `adapter` string
@@ -145,6 +149,8 @@ uint64_t mirge_hash_sequence(const char *seq, int len);
 int mirge_profile_enable(mirge_ctx *ctx, int on);
 /* ms[k], launches[k] accumulated since enable; names[k] static strings. */
 int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const char **names);
+/* Number of kernels this library has launched on the context so far. */
+uint64_t mirge_launch_count(const mirge_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,7 @@ struct mirge_ctx {
     std::vector<ProfSpan> spans;
     double prof_ms[MIRGE_N_KERNELS];
     uint64_t prof_n[MIRGE_N_KERNELS];
+    uint64_t n_launches = 0;
 };
 
 static thread_local std::string g_create_err;
@@ -95,10 +96,12 @@ static thread_local std::string g_create_err;
 
 static int fail(mirge_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
 
+// Brackets `launches` kernel launches of family `kid` (CUDA events when profiling is on).
 struct ProfScope {
     mirge_ctx *c; int kid; cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(mirge_ctx *c_, int kid_) : c(c_), kid(kid_)
+    ProfScope(mirge_ctx *c_, int kid_, int launches = 1) : c(c_), kid(kid_)
     {
+        c->n_launches += launches;
         if (c->prof) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
     }
     ~ProfScope()
@@ -295,8 +298,8 @@ static int feed_device_impl(mirge_ctx *ctx, int sample, const unsigned char *d_t
     { ProfScope ps(ctx, KID_K0_COUNT);
       CK(cudaMemsetAsync(ctx->d_tile + ntiles, 0, sizeof(u32), st));
       k0_count_newlines<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, nbytes, ctx->d_tile); }
-    { ProfScope ps(ctx, KID_K0_SCAN);
-      device_excl_scan(ctx->d_tile, ctx->d_tile, ntiles + 1, ctx->d_scan, st); }
+    { ProfScope ps(ctx, KID_K0_SCAN, 0);
+      ctx->n_launches += device_excl_scan(ctx->d_tile, ctx->d_tile, ntiles + 1, ctx->d_scan, st); }
     u32 n_newlines = 0;
     CK(cudaMemcpyAsync(&n_newlines, ctx->d_tile + ntiles, sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -316,7 +319,7 @@ static int feed_device_impl(mirge_ctx *ctx, int sample, const unsigned char *d_t
     { ProfScope ps(ctx, KID_K0_LINES);
       CK(cudaMemsetAsync(ctx->d_lines, 0, sizeof(u32), st));
       k0_line_starts<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, nbytes, ctx->d_tile, ctx->d_lines);
-      if (last_char != '\n') k_set_u32<<<1, 1, 0, st>>>(ctx->d_lines + n_lines, (u32)(nbytes + 1)); }
+      if (last_char != '\n') { k_set_u32<<<1, 1, 0, st>>>(ctx->d_lines + n_lines, (u32)(nbytes + 1)); ctx->n_launches++; } }
     K0Params kp; kp.phred_base = phred_base; kp.qual_cutoff = ctx->qual_cutoff; kp.max_len = ctx->max_len;
     { ProfScope ps(ctx, KID_K0_PACK);
       k0_pack<W><<<grid_for(nrec, 256, 148 * 16), 256, 0, st>>>(d_text, ctx->d_lines, nrec, kp, ctx->d_bases, ctx->d_nmask,
@@ -349,7 +352,7 @@ int mirge_feed_fastq(mirge_ctx *ctx, int sample, const char *fastq, uint64_t nby
     if (nbytes == 0) return MIRGE_OK;
     CK(cudaSetDevice(ctx->device));
     CK(ensure(&ctx->d_text, &ctx->text_cap, (size_t)nbytes + 64));
-    { ProfScope ps(ctx, KID_H2D);
+    { ProfScope ps(ctx, KID_H2D, 0);
       CK(cudaMemcpyAsync(ctx->d_text, fastq, nbytes, cudaMemcpyHostToDevice, ctx->stream)); }
     const int last = (unsigned char)fastq[nbytes - 1];
     return ctx->W == 2 ? feed_device_impl<2>(ctx, sample, ctx->d_text, nbytes, phred_base, last)
@@ -384,7 +387,7 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
     CK(cudaStreamSynchronize(st));
     DevLib &l = ctx->libs[lib_id];
     free_lib(l);
-    ProfScope ps(ctx, KID_LIB_BUILD);
+    ProfScope ps(ctx, KID_LIB_BUILD, 0);
     l.n_refs = n_refs; l.total = (u32)total;
     const size_t nw64 = (total + 63) / 64;
     CK(cudaMalloc(&l.seq, (2 * nw64 + 8) * sizeof(u64)));
@@ -525,11 +528,11 @@ int mirge_tally(mirge_ctx *ctx)
     while ((1 << bits) < n_seg) bits++;
     int cur = 0;
     if (n_tiles) {
-        ProfScope ps(ctx, KID_K3_SORT);
+        ProfScope ps(ctx, KID_K3_SORT, 0);
         const int gt = (int)(n_tiles < 148u * 8u ? n_tiles : 148u * 8u);
         for (int shift = 0; shift < bits; shift += 8) {
             k3_rs_hist<<<gt, RS_THREADS, 0, st>>>(keys[cur], ctx->d_ctr, shift, n_tiles, hist);
-            device_excl_scan(hist, hist, hist_n, scratch, st);
+            ctx->n_launches += 2 + device_excl_scan(hist, hist, hist_n, scratch, st);
             k3_rs_scatter<<<gt, RS_THREADS, 0, st>>>(keys[cur], vals[cur], ctx->d_ctr, shift, n_tiles, hist, keys[cur ^ 1], vals[cur ^ 1]);
             cur ^= 1;
         }
@@ -636,7 +639,7 @@ int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint
     CK(cudaMemsetAsync(d_cnt, 0, 2 * (size_t)n_parts * sizeof(u64), st));
     const int rb = mirge_record_bytes(ctx), g = grid_for(U, 128, 148 * 8);
     {
-        ProfScope ps(ctx, KID_EXCHANGE);
+        ProfScope ps(ctx, KID_EXCHANGE, 3);
         if (ctx->W == 2) {
             k1_export_records<2><<<g, 128, 0, st>>>(table_view<2>(ctx), U, n_parts, rb, 1, d_cnt, nullptr, nullptr);
             k_excl_scan_small<<<1, 1, 0, st>>>(d_cnt, d_cnt + n_parts, n_parts);
@@ -653,6 +656,20 @@ int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint
     CK(cudaGetLastError());
     return MIRGE_OK;
 }
+
+int mirge_reset(mirge_ctx *ctx)
+{
+    int rc = mirge_reset_unique(ctx);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (2 + (size_t)ctx->S) * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * ctx->S * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), st));
+    ctx->processed.assign(ctx->S, 0);
+    return MIRGE_OK;
+}
+
+uint64_t mirge_launch_count(const mirge_ctx *ctx) { return ctx->n_launches; }
 
 int mirge_reset_unique(mirge_ctx *ctx)
 {

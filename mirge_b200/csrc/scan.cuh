@@ -44,16 +44,18 @@ static inline u64 scan_scratch_elems(u64 n)
 }
 
 // Exclusive scan of in[0..n) into out[0..n).  scratch must hold scan_scratch_elems(n) u32.
-static void device_excl_scan(const u32 *in, u32 *out, u64 n, u32 *scratch, cudaStream_t st)
+// Returns the number of kernels launched.
+static int device_excl_scan(const u32 *in, u32 *out, u64 n, u32 *scratch, cudaStream_t st)
 {
-    if (n == 0) return;
+    if (n == 0) return 0;
     u64 nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     if (nb == 1) {
         scan_block_apply<<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr);
-        return;
+        return 1;
     }
     u32 *sums = scratch;
     scan_block_sums<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, sums);
-    device_excl_scan(sums, sums, nb, scratch + nb + 1, st);
+    int k = device_excl_scan(sums, sums, nb, scratch + nb + 1, st);
     scan_block_apply<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, n, sums);
+    return k + 2;
 }

@@ -153,6 +153,12 @@ class Engine:
         self._ck(lib.mirge_export_records_device(self.h, n_parts, C.c_void_p(int(dev_ptr)), int(cap_records), _ptr(pc)))
         return pc
 
+    def reset(self):
+        self._ck(lib.mirge_reset(self.h))
+
+    def launch_count(self):
+        return int(lib.mirge_launch_count(self.h))
+
     def reset_unique(self):
         self._ck(lib.mirge_reset_unique(self.h))
 

@@ -495,6 +495,19 @@ int orc_trim_fastq(OrcCtx *c, const char *buf, uint64_t n, int phred_base, int32
     return (int)r;
 }
 
+/* Forget reads and unique sequences; keep adapter and libraries (bench loops). */
+void orc_reset(OrcCtx *c)
+{
+    OrcUniq *u = &c->uq;
+    free(u->arena); free(u->seq_off); free(u->seq_len); free(u->counts);
+    free(u->round_of); free(u->ref_of); free(u->pos_of); free(u->mm_of);
+    free(u->map.hash); free(u->map.uid);
+    memset(u, 0, sizeof *u);
+    memset(c->len_hist, 0, (size_t)(ORC_MAX_READLEN + 1) * (size_t)c->n_samples * sizeof(uint64_t));
+    memset(c->processed, 0, (size_t)c->n_samples * sizeof(uint64_t));
+    memset(c->kept, 0, (size_t)c->n_samples * sizeof(uint64_t));
+}
+
 uint64_t orc_n_unique(OrcCtx *c) { return c->uq.n_unique; }
 uint64_t orc_seq_bytes(OrcCtx *c) { return c->uq.arena_len; }
 

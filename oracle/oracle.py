@@ -49,6 +49,7 @@ def lib():
         L.orc_detect_phred.argtypes = [C.c_char_p, C.c_uint64]
         L.orc_feed_fastq.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_int, C.c_int]
         L.orc_trim_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_reset.argtypes = [C.c_void_p]
         L.orc_n_unique.restype = C.c_uint64
         L.orc_n_unique.argtypes = [C.c_void_p]
         L.orc_seq_bytes.restype = C.c_uint64
@@ -163,6 +164,9 @@ class Oracle:
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError(lib().orc_last_error(self.h).decode())
+
+    def reset(self):
+        lib().orc_reset(self.h)
 
     def set_adapter(self, spec):
         self._check(lib().orc_set_adapter(self.h, spec.encode()))
