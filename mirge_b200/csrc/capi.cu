@@ -16,6 +16,7 @@
 #include "scan.cuh"
 #include "k0_parse.cuh"
 #include "k1_trim.cuh"
+#include "k1_kernel.cuh"
 #include "k2_map.cuh"
 #include "k3_tally.cuh"
 
@@ -47,7 +48,9 @@ struct mirge_ctx {
     std::string err;
     // trim configuration
     TrimParams tp;
+    K1Thr thr;
     int qual_cutoff = 10;
+    int force_slow = 0;
     // K0 scratch
     unsigned char *d_text = nullptr; size_t text_cap = 0;
     u32 *d_tile = nullptr; size_t tile_cap = 0;
@@ -59,7 +62,7 @@ struct mirge_ctx {
     u64 max_unique = 0;
     u64 *d_useq = nullptr, *d_unmask = nullptr; u8 *d_ulen = nullptr; u32 *d_counts = nullptr;
     signed char *d_round_of = nullptr, *d_mm_of = nullptr; int *d_ref_of = nullptr, *d_pos_of = nullptr;
-    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept
+    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept, [2+S] slow-path reads
     u64 *d_ctr = nullptr;
     u64 *d_len_hist = nullptr;
     std::vector<u64> processed;
@@ -176,7 +179,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_mm_of, max_unique));
     CK(cudaMalloc(&ctx->d_ref_of, max_unique * sizeof(int)));
     CK(cudaMalloc(&ctx->d_pos_of, max_unique * sizeof(int)));
-    CK(cudaMalloc(&ctx->d_ctr, (2 + (size_t)n_samples) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_ctr, (3 + (size_t)n_samples) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_len_hist, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_todo[0], max_unique * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_todo[1], max_unique * sizeof(u32)));
@@ -185,7 +188,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_lib_totals, (size_t)n_samples * MIRGE_N_TOTALS * sizeof(i64)));
     CK(cudaMemsetAsync(ctx->d_slots, 0, cap * esz, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counts, 0, max_unique * (size_t)n_samples * sizeof(u32), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_ctr, 0, (2 + (size_t)n_samples) * sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (3 + (size_t)n_samples) * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -273,6 +276,12 @@ int mirge_set_adapter(mirge_ctx *ctx, const char *spec, double error_rate, int m
         }
     }
     ctx->tp = tp;
+    for (int i = 0; i <= MIRGE_MAX_ADAPTER_LEN; i++) {
+        // cutadapt accepts a candidate of length i iff i >= min_overlap and cost <= i * max_error_rate (double)
+        int c = -1;
+        if (i >= min_overlap) { c = 0; while ((double)(c + 1) <= (double)i * error_rate) c++; }
+        ctx->thr.v[i] = (signed char)c;
+    }
     ctx->qual_cutoff = qual_cutoff;
     return MIRGE_OK;
 }
@@ -324,10 +333,10 @@ static int feed_device_impl(mirge_ctx *ctx, int sample, const unsigned char *d_t
     { ProfScope ps(ctx, KID_K0_PACK);
       k0_pack<W><<<grid_for(nrec, 256, 148 * 16), 256, 0, st>>>(d_text, ctx->d_lines, nrec, kp, ctx->d_bases, ctx->d_nmask,
                                                                ctx->d_meta, (u32 *)(ctx->d_ctr + 1)); }
-    K1Counters kc; kc.kept = ctx->d_ctr + 2; kc.len_hist = ctx->d_len_hist;
+    K1Counters kc; kc.kept = ctx->d_ctr + 2; kc.len_hist = ctx->d_len_hist; kc.slow_reads = ctx->d_ctr + 2 + ctx->S;
     { ProfScope ps(ctx, KID_K1_TRIM);
       k1_trim_collapse<W><<<grid_for(nrec, 128, 148 * 16), 128, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample,
-                                                                        ctx->tp, table_view<W>(ctx), kc); }
+                                                                        ctx->tp, ctx->thr, table_view<W>(ctx), kc, ctx->force_slow); }
     CK(cudaGetLastError());
     ctx->processed[sample] += nrec;
     ctx->annotated = false; ctx->tallied = false;
@@ -662,7 +671,7 @@ int mirge_reset(mirge_ctx *ctx)
     int rc = mirge_reset_unique(ctx);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_ctr, 0, (2 + (size_t)ctx->S) * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (3 + (size_t)ctx->S) * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * ctx->S * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), st));
     ctx->processed.assign(ctx->S, 0);
@@ -670,6 +679,17 @@ int mirge_reset(mirge_ctx *ctx)
 }
 
 uint64_t mirge_launch_count(const mirge_ctx *ctx) { return ctx->n_launches; }
+
+int mirge_debug(mirge_ctx *ctx, int force_slow, uint64_t *slow_reads)
+{
+    if (force_slow >= 0) ctx->force_slow = force_slow;
+    if (slow_reads) {
+        int rc = mirge_sync(ctx);
+        if (rc) return rc;
+        CK(cudaMemcpy(slow_reads, ctx->d_ctr + 2 + ctx->S, sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    return MIRGE_OK;
+}
 
 int mirge_reset_unique(mirge_ctx *ctx)
 {

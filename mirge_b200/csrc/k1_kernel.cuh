@@ -1,0 +1,264 @@
+// k1_kernel.cuh -- the fused trim + collapse kernel (K1).
+//
+// Per read (one thread each, packed record streamed with one 128-bit load):
+//   1. apply the quality-trim window computed by K0;
+//   2. find the 3' adapter exactly as cutadapt would:
+//        fast path  - Myers' bit-vector edit distance (the <=32-nt adapter is one
+//                     machine word) gives the cost of EVERY DP cell of the last
+//                     columns; the few candidate end cells cutadapt ranks by
+//                     (matches, cost, visiting order) are resolved by walking
+//                     cutadapt's own predecessor preference (diagonal, then
+//                     insertion, then deletion) backwards until a zero-cost cell,
+//                     reading cell costs from the bit-vectors of the last 8
+//                     columns (kept in shared memory);
+//        slow path  - reads whose candidates cannot be settled inside that
+//                     window (sequencing errors deep inside the adapter, a full
+//                     inexact adapter occurrence, adapters > 32 nt) are queued
+//                     per CTA and run through the literal banded DP
+//                     (locate_back) by fully converged warps;
+//   3. length filter, then insert into the unique-sequence table.
+// Both paths return cutadapt's rstart; parity tests compare them read by read.
+#pragma once
+#include "common.cuh"
+#include "k1_trim.cuh"
+
+#define K1_THREADS 128
+#define K1_RING 8
+#define K1_QCAP (3 * K1_THREADS)
+
+struct K1Counters {
+    u64 *kept;        // [S]
+    u64 *len_hist;    // [(max_len + 1)][S]
+    u64 *slow_reads;  // diagnostic: reads that took the slow path
+};
+
+// thr[i] = largest cost c with c <= i * error_rate (double), or -1 below min_overlap
+struct K1Thr { signed char v[MIRGE_MAX_ADAPTER_LEN + 1]; };
+
+template <int W>
+__device__ __forceinline__ void k1_load_record(const u64 *__restrict__ bases, const u64 *__restrict__ nmask,
+                                               const u32 *__restrict__ meta, u64 r, PSeq<W> &p, int &n)
+{
+    if (W == 2) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(bases) + r);
+        p.s[0] = v.x; p.s[1] = v.y;
+    } else {
+#pragma unroll
+        for (int w = 0; w < W; w++) p.s[w] = __ldg(bases + r * W + w);
+    }
+#pragma unroll
+    for (int w = 0; w < W / 2; w++) p.nm[w] = __ldg(nmask + r * (W / 2) + w);
+    const u32 mt = __ldg(meta + r);
+    const int qstart = (mt >> 8) & 0xFF, qstop = (mt >> 16) & 0xFF;
+    n = qstop - qstart;
+    pseq_shift<W>(p, qstart);
+    pseq_truncate<W>(p, n);
+}
+
+// cost of DP cell (i, j) from the ring of column bit-vectors; column 0 is cost i.
+__device__ __forceinline__ int k1_cell_cost(const u64 *ring, int i, int j)
+{
+    if (j == 0) return i;
+    const u64 v = ring[(j & (K1_RING - 1)) * K1_THREADS];
+    const u32 low = (i >= 32) ? 0xFFFFFFFFu : ((1u << i) - 1u);
+    return __popc((u32)v & low) - __popc((u32)(v >> 32) & low);
+}
+
+#define K1_NOMATCH (-1)
+#define K1_SLOW (-2)
+
+// Fast adapter search for one adapter of length m <= 32.
+// Returns rstart >= 0 (matches in matches_out), K1_NOMATCH, or K1_SLOW.
+// `ring` points at this thread's column slot 0 (stride K1_THREADS between slots).
+template <int W>
+__device__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, const K1Thr &thr, int a, u64 *ring,
+                             int &matches_out)
+{
+    const int m = tp.alen[a];
+    const u32 pe0 = (u32)tp.peq[a][0], pe1 = (u32)tp.peq[a][1], pe2 = (u32)tp.peq[a][2], pe3 = (u32)tp.peq[a][3];
+    u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
+    int score = m;
+    const int thr_m = thr.v[m];
+    bool full_cand = false;
+    const int win_lo = n - (K1_RING - 1);          // first column kept in the ring
+    u64 sw = p.s[0], nw = p.nm[0];
+    for (int j = 1; j <= n; j++) {
+        const int b = j - 1;
+        if ((b & 31) == 0 && b) {
+#pragma unroll
+            for (int w = 1; w < W; w++) if ((b >> 5) == w) sw = p.s[w];
+        }
+        if ((b & 63) == 0 && b) {
+#pragma unroll
+            for (int w = 1; w < W / 2; w++) if ((b >> 6) == w) nw = p.nm[w];
+        }
+        const u32 c = (u32)(sw & 3ull);
+        sw >>= 2;
+        const bool isn = (nw & 1ull) != 0;
+        nw >>= 1;
+        u32 Eq = c == 0 ? pe0 : c == 1 ? pe1 : c == 2 ? pe2 : pe3;
+        if (isn) Eq = 0;
+        const u32 Xv = Eq | Mv;
+        const u32 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        u32 Ph = Mv | ~(Xh | Pv);
+        u32 Mh = Pv & Xh;
+        score += (int)((Ph >> (m - 1)) & 1u) - (int)((Mh >> (m - 1)) & 1u);
+        Ph <<= 1; Mh <<= 1;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+        if (j >= win_lo) ring[(j & (K1_RING - 1)) * K1_THREADS] = (u64)Pv | ((u64)Mv << 32);
+        if (score == 0) { matches_out = m; return j - m; }        // str.find: leftmost exact occurrence
+        if (score <= thr_m) full_cand = true;
+    }
+    if (full_cand) return K1_SLOW;     // an inexact full-length occurrence competes: literal DP decides
+    // partial candidates (adapter prefix i at the read's end), visited i = m .. 0
+    u64 valid = 0;
+    {
+        int c = 0;
+        for (int i = 1; i <= m; i++) {
+            c += (int)((Pv >> (i - 1)) & 1u) - (int)((Mv >> (i - 1)) & 1u);
+            if (c <= thr.v[i]) valid |= 1ull << i;
+        }
+    }
+    int best_m = 0, best_c = m + n, best_o = K1_NOMATCH;
+    while (valid) {
+        const int i = 63 - __clzll(valid);
+        valid &= ~(1ull << i);
+        if (i < best_m) break;                      // matches <= i: cannot win any more
+        const int c = k1_cell_cost(ring, i, n);
+        if (i == best_m && c >= best_c) continue;   // could at best tie on matches with no better cost
+        int mt, o;
+        if (c == 0) {
+            mt = i; o = n - i;
+        } else {
+            // walk cutadapt's predecessor choice back to a zero-cost (exact) cell
+            int ci = i, cj = n, cc = c;
+            mt = 0; o = -1;
+            for (;;) {
+                if (ci == 0) { o = cj; break; }
+                if (cc == 0) { mt += ci; o = cj - ci; break; }
+                if (cj == 0) { o = 0; break; }
+                const int rb = pseq_isn<W>(p, cj - 1) ? 4 : pseq_base<W>(p, cj - 1);
+                const int ab = (int)((tp.aw[a][0] >> ((ci - 1) * 2)) & 3ull);
+                if (rb == ab) { mt++; ci--; cj--; continue; }
+                if (cj < win_lo || (cj - 1 != 0 && cj - 1 < win_lo)) return K1_SLOW;   // needs a column outside the window
+                const int cd = k1_cell_cost(ring, ci - 1, cj - 1) + 1;
+                const int cdel = k1_cell_cost(ring, ci, cj - 1) + 1;
+                const int cins = k1_cell_cost(ring, ci - 1, cj) + 1;
+                if (cd <= cdel && cd <= cins) { ci--; cj--; cc = cd - 1; }
+                else if (cins <= cdel) { ci--; cc = cins - 1; }
+                else { cj--; cc = cdel - 1; }
+            }
+        }
+        if (mt > best_m || (mt == best_m && c < best_c)) { best_m = mt; best_c = c; best_o = o; }
+    }
+    matches_out = best_m;
+    return best_o;
+}
+
+// AdapterCutter(times=1) over all adapters: most matches wins, first wins ties.
+// Returns the new length, or K1_SLOW.
+template <int W>
+__device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimParams &tp, const K1Thr &thr, u64 *ring)
+{
+    int best_rstart = -1, best_matches = -1;
+    for (int a = 0; a < tp.n_adapters; a++) {
+        if (tp.alen[a] > 32) return K1_SLOW;
+        int mt = 0;
+        const int rs = k1_match_fast<W>(p, n, tp, thr, a, ring, mt);
+        if (rs == K1_SLOW) return K1_SLOW;
+        if (rs >= 0 && (best_rstart < 0 || mt > best_matches)) { best_rstart = rs; best_matches = mt; }
+    }
+    return best_rstart >= 0 ? best_rstart : n;
+}
+
+template <int W>
+__device__ __forceinline__ int k1_trim_slow(const PSeq<W> &p, int n, const TrimParams &tp)
+{
+    int best_rstart = -1, best_matches = -1;
+    for (int a = 0; a < tp.n_adapters; a++) {
+        int rs, mt;
+        if (match_back<W>(p, n, tp, a, rs, mt) && (best_rstart < 0 || mt > best_matches)) { best_rstart = rs; best_matches = mt; }
+    }
+    return best_rstart >= 0 ? best_rstart : n;
+}
+
+template <int W>
+__device__ __forceinline__ bool k1_finish(PSeq<W> &p, int n, const TrimParams &tp, const TableView<W> &T, int sample, u32 *sh_hist)
+{
+    if (n < tp.min_length) return false;
+    pseq_truncate<W>(p, n);
+    const u64 h = pseq_hash<W>(p, n);
+    const u32 id = table_upsert<W>(T, p, n, h);
+    if (id != 0xFFFFFFFFu) atomicAdd(&T.counts[(u64)id * T.S + sample], 1u);
+    atomicAdd(&sh_hist[n], 1u);
+    return true;
+}
+
+// force_slow != 0 routes every read through the literal DP (parity tests).
+template <int W>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
+                 u64 n_records, int sample, TrimParams tp, K1Thr thr, TableView<W> T, K1Counters ctr, int force_slow)
+{
+    __shared__ u64 ring[K1_RING * K1_THREADS];
+    __shared__ u32 slowq[K1_QCAP];
+    __shared__ u32 slowq_n;
+    __shared__ u32 sh_hist[32 * W + 1];
+    for (int b = threadIdx.x; b <= 32 * W; b += K1_THREADS) sh_hist[b] = 0;
+    if (threadIdx.x == 0) slowq_n = 0;
+    __syncthreads();
+    u32 my_kept = 0, my_slow = 0;
+    u64 *my_ring = ring + threadIdx.x;
+    for (u64 r0 = (u64)blockIdx.x * K1_THREADS; r0 < n_records; r0 += (u64)gridDim.x * K1_THREADS) {
+        const u64 r = r0 + threadIdx.x;
+        if (r < n_records) {
+            PSeq<W> p;
+            int n;
+            k1_load_record<W>(bases, nmask, meta, r, p, n);
+            int nf = n;
+            if (tp.mode == 2) {
+                const int L = tp.uncond;
+                if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); nf = n - cut; }
+                else if (L < 0) { const int cut = (-L) < n ? (-L) : n; nf = n - cut; }
+            } else if (tp.mode == 1) {
+                nf = force_slow ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring);
+            }
+            if (nf == K1_SLOW) {
+                slowq[atomicAdd(&slowq_n, 1u)] = (u32)r;
+            } else {
+                my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        // drain the slow queue with converged threads once it could overflow on the next
+        // tile (every tile adds at most K1_THREADS entries), and after the last tile
+        const u32 qn = slowq_n;
+        const bool last_tile = r0 + (u64)gridDim.x * K1_THREADS >= n_records;
+        if (qn && (qn > K1_QCAP - K1_THREADS || last_tile)) {
+            for (u32 q = threadIdx.x; q < qn; q += K1_THREADS) {
+                PSeq<W> p;
+                int n;
+                k1_load_record<W>(bases, nmask, meta, (u64)slowq[q], p, n);
+                const int nf = k1_trim_slow<W>(p, n, tp);
+                my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
+                my_slow++;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) slowq_n = 0;
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        my_kept += __shfl_down_sync(0xffffffffu, my_kept, d);
+        my_slow += __shfl_down_sync(0xffffffffu, my_slow, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (my_kept) atomicAdd(&ctr.kept[sample], (u64)my_kept);
+        if (my_slow && ctr.slow_reads) atomicAdd(ctr.slow_reads, (u64)my_slow);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b <= 32 * W; b += K1_THREADS)
+        if (sh_hist[b]) atomicAdd(&ctr.len_hist[(u64)b * T.S + sample], (u64)sh_hist[b]);
+}

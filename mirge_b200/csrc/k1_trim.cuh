@@ -216,64 +216,6 @@ __device__ __forceinline__ bool match_back(const PSeq<W> &p, int n, const TrimPa
     return locate_back<W>(p, n, tp.aw[a], m, tp.error_rate, tp.min_overlap, rstart, matches);
 }
 
-struct K1Counters {
-    u64 *kept;        // [S]
-    u64 *len_hist;    // [(max_len + 1)][S]
-};
-
-template <int W>
-__global__ void __launch_bounds__(128)
-k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-                 u64 n_records, int sample, TrimParams tp, TableView<W> T, K1Counters ctr)
-{
-    const int NW = W / 2;
-    for (u64 r0 = (u64)blockIdx.x * blockDim.x; r0 < n_records; r0 += (u64)gridDim.x * blockDim.x) {
-        const u64 r = r0 + threadIdx.x;
-        bool kept = false;
-        int n = 0;
-        PSeq<W> p;
-        if (r < n_records) {
-            if (W == 2) {
-                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(bases) + r);
-                p.s[0] = v.x; p.s[1] = v.y;
-            } else {
-#pragma unroll
-                for (int w = 0; w < W; w++) p.s[w] = __ldg(bases + r * W + w);
-            }
-#pragma unroll
-            for (int w = 0; w < NW; w++) p.nm[w] = __ldg(nmask + r * NW + w);
-            const u32 mt = __ldg(meta + r);
-            const int qstart = (mt >> 8) & 0xFF, qstop = (mt >> 16) & 0xFF;
-            n = qstop - qstart;
-            pseq_shift<W>(p, qstart);
-            pseq_truncate<W>(p, n);
-            if (tp.mode == 2) {
-                const int L = tp.uncond;
-                if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); n -= cut; }
-                else if (L < 0) { const int cut = (-L) < n ? (-L) : n; n -= cut; pseq_truncate<W>(p, n); }
-            } else if (tp.mode == 1) {
-                int best_rstart = -1, best_matches = -1;
-                for (int a = 0; a < tp.n_adapters; a++) {
-                    int rs, mt2;
-                    if (match_back<W>(p, n, tp, a, rs, mt2) && (best_rstart < 0 || mt2 > best_matches)) {
-                        best_rstart = rs; best_matches = mt2;
-                    }
-                }
-                if (best_rstart >= 0) { n = best_rstart; pseq_truncate<W>(p, n); }
-            }
-            kept = n >= tp.min_length;
-        }
-        if (kept) {
-            const u64 h = pseq_hash<W>(p, n);
-            const u32 id = table_upsert<W>(T, p, n, h);
-            if (id != 0xFFFFFFFFu) atomicAdd(&T.counts[(u64)id * T.S + sample], 1u);
-            atomicAdd(&ctr.len_hist[(u64)n * T.S + sample], 1ull);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, kept);
-        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&ctr.kept[sample], (u64)__popc(bal));
-    }
-}
-
 // Insert exchange records (multi-GPU): record = W + W/2 u64 words, then
 // u32 len, then S u32 counts, padded to 8 bytes.
 template <int W>

@@ -159,6 +159,15 @@ class Engine:
     def launch_count(self):
         return int(lib.mirge_launch_count(self.h))
 
+    def force_slow_path(self, on=True):
+        """Test hook: run every read through the literal cutadapt DP."""
+        self._ck(lib.mirge_debug(self.h, int(on), None))
+
+    def slow_reads(self):
+        n = np.zeros(1, np.uint64)
+        self._ck(lib.mirge_debug(self.h, -1, _ptr(n)))
+        return int(n[0])
+
     def reset_unique(self):
         self._ck(lib.mirge_reset_unique(self.h))
 
