@@ -229,6 +229,7 @@ def run_ours(args):
     sampler.stop_flag = True
     # size-independent correctness properties at full size (tests/ hold the bit-exact oracle comparisons)
     p, k, U = eng.stats()
+    slow_frac = eng.slow_reads() / float(n_reads)
     tabs = eng.export_tables()
     if N > 1:
         tabs = mdist.reduce_tables({kk: tabs[kk] for kk in ('lib_totals',)}, dev)
@@ -271,7 +272,7 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': 'reads/s', 'n_gpus': N, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u8/u64 (2-bit packed integer)', 'data': 'synthetic',
-            'config': {'workload': workload_name(args), 'reads_per_gpu': n_reads, 'unique_per_gpu': U, 'kept_frac': float(k[sample]) / n_reads,
+            'config': {'workload': workload_name(args), 'reads_per_gpu': n_reads, 'unique_per_gpu': U, 'kept_frac': float(k[sample]) / n_reads, 'k1_slow_path_frac': slow_frac,
                        'l2_policy': 'inputs (%.2f GB FASTQ text per GPU) larger than the 126 MB L2' % (nbytes / 1e9),
                        'parallelism': 'reads sharded by sample across %d GPU(s); hash-partition all-to-all + table all-reduce' % N},
             'e2e': {'value': e2e, 'unit': 'reads/s', 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},

@@ -79,8 +79,9 @@ __device__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, cons
     u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
     int score = m;
     const int thr_m = thr.v[m];
-    bool full_cand = false;
     const int win_lo = n - (K1_RING - 1);          // first column kept in the ring
+    u32 full_mask = 0;                             // bit (j - win_lo): inexact full-length candidate ending at column j
+    bool deep_full = false;
     u64 sw = p.s[0], nw = p.nm[0];
     for (int j = 1; j <= n; j++) {
         const int b = j - 1;
@@ -108,10 +109,15 @@ __device__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, cons
         Mv = Ph & Xv;
         if (j >= win_lo) ring[(j & (K1_RING - 1)) * K1_THREADS] = (u64)Pv | ((u64)Mv << 32);
         if (score == 0) { matches_out = m; return j - m; }        // str.find: leftmost exact occurrence
-        if (score <= thr_m) full_cand = true;
+        if (score <= thr_m) {
+            if (j >= win_lo) full_mask |= 1u << (j - win_lo); else deep_full = true;
+        }
     }
-    if (full_cand) return K1_SLOW;     // an inexact full-length occurrence competes: literal DP decides
-    // partial candidates (adapter prefix i at the read's end), visited i = m .. 0
+    if (deep_full) return K1_SLOW;     // an inexact full-length occurrence far from the read end: literal DP decides
+    // cutadapt keeps the candidate with most matches, then lowest cost, then first
+    // visited: full-length candidates by ascending end column, then adapter
+    // prefixes i = m .. 0 ending at the read's end.
+    int best_m = 0, best_c = m + n, best_o = K1_NOMATCH, best_v = 0x7fffffff;
     u64 valid = 0;
     {
         int c = 0;
@@ -120,19 +126,28 @@ __device__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, cons
             if (c <= thr.v[i]) valid |= 1ull << i;
         }
     }
-    int best_m = 0, best_c = m + n, best_o = K1_NOMATCH;
-    while (valid) {
-        const int i = 63 - __clzll(valid);
-        valid &= ~(1ull << i);
-        if (i < best_m) break;                      // matches <= i: cannot win any more
-        const int c = k1_cell_cost(ring, i, n);
-        if (i == best_m && c >= best_c) continue;   // could at best tie on matches with no better cost
+    for (;;) {
+        int i, j, visit;
+        if (full_mask) {
+            const int t = __ffs(full_mask) - 1;
+            full_mask &= full_mask - 1;
+            i = m; j = win_lo + t; visit = j;
+        } else if (valid) {
+            i = 63 - __clzll(valid);
+            valid &= ~(1ull << i);
+            if (i < best_m) break;                      // matches <= i: cannot win any more
+            j = n; visit = n + 1 + (m - i);
+        } else {
+            break;
+        }
+        const int c = k1_cell_cost(ring, i, j);
+        if (j == n && i == best_m && c >= best_c) continue;   // could at best tie, and was visited later
         int mt, o;
         if (c == 0) {
-            mt = i; o = n - i;
+            mt = i; o = j - i;
         } else {
             // walk cutadapt's predecessor choice back to a zero-cost (exact) cell
-            int ci = i, cj = n, cc = c;
+            int ci = i, cj = j, cc = c;
             mt = 0; o = -1;
             for (;;) {
                 if (ci == 0) { o = cj; break; }
@@ -150,7 +165,9 @@ __device__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, cons
                 else { cj--; cc = cdel - 1; }
             }
         }
-        if (mt > best_m || (mt == best_m && c < best_c)) { best_m = mt; best_c = c; best_o = o; }
+        if (mt > best_m || (mt == best_m && (c < best_c || (c == best_c && visit < best_v)))) {
+            best_m = mt; best_c = c; best_o = o; best_v = visit;
+        }
     }
     matches_out = best_m;
     return best_o;
