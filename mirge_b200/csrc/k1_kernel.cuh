@@ -67,125 +67,147 @@ __device__ __forceinline__ int k1_cell_cost(const u64 *ring, int i, int j)
 #define K1_NOMATCH (-1)
 #define K1_SLOW (-2)
 
-// Fast adapter search for one adapter of length m <= 32.
+// Fast adapter search for one adapter of length m <= 32, executed by all 32
+// lanes of a warp in lock step (every loop has a warp-uniform trip count, so
+// lanes never serialise behind each other's data-dependent work).
 // Returns rstart >= 0 (matches in matches_out), K1_NOMATCH, or K1_SLOW.
 // `ring` points at this thread's column slot 0 (stride K1_THREADS between slots).
 template <int W>
-__device__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, const K1Thr &thr, int a, u64 *ring,
-                             int &matches_out)
+__device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, int a,
+                                             u64 *ring, int &matches_out)
 {
     const int m = tp.alen[a];
+    const u64 aw = tp.aw[a][0];
     const u32 pe0 = (u32)tp.peq[a][0], pe1 = (u32)tp.peq[a][1], pe2 = (u32)tp.peq[a][2], pe3 = (u32)tp.peq[a][3];
     u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
     int score = m;
-    const int thr_m = thr.v[m];
+    const int thr_m = thr[m];
     const int win_lo = n - (K1_RING - 1);          // first column kept in the ring
     u32 full_mask = 0;                             // bit (j - win_lo): inexact full-length candidate ending at column j
-    bool deep_full = false;
-    u64 sw = p.s[0], nw = p.nm[0];
-    for (int j = 1; j <= n; j++) {
-        const int b = j - 1;
-        if ((b & 31) == 0 && b) {
+    bool slow = false;
+    int exact_j = -1;
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
+    {
+        PSeq<W> q = p;                             // consumed base by base
+        for (int j = 1; j <= nmax; j++) {
+            const u32 c = (u32)(q.s[0] & 3ull);
+            const bool isn = (q.nm[0] & 1ull) != 0;
 #pragma unroll
-            for (int w = 1; w < W; w++) if ((b >> 5) == w) sw = p.s[w];
-        }
-        if ((b & 63) == 0 && b) {
+            for (int w = 0; w < W; w++) q.s[w] = (q.s[w] >> 2) | (w + 1 < W ? (q.s[w + 1 < W ? w + 1 : w] << 62) : 0ull);
 #pragma unroll
-            for (int w = 1; w < W / 2; w++) if ((b >> 6) == w) nw = p.nm[w];
-        }
-        const u32 c = (u32)(sw & 3ull);
-        sw >>= 2;
-        const bool isn = (nw & 1ull) != 0;
-        nw >>= 1;
-        u32 Eq = c == 0 ? pe0 : c == 1 ? pe1 : c == 2 ? pe2 : pe3;
-        if (isn) Eq = 0;
-        const u32 Xv = Eq | Mv;
-        const u32 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-        u32 Ph = Mv | ~(Xh | Pv);
-        u32 Mh = Pv & Xh;
-        score += (int)((Ph >> (m - 1)) & 1u) - (int)((Mh >> (m - 1)) & 1u);
-        Ph <<= 1; Mh <<= 1;
-        Pv = Mh | ~(Xv | Ph);
-        Mv = Ph & Xv;
-        if (j >= win_lo) ring[(j & (K1_RING - 1)) * K1_THREADS] = (u64)Pv | ((u64)Mv << 32);
-        if (score == 0) { matches_out = m; return j - m; }        // str.find: leftmost exact occurrence
-        if (score <= thr_m) {
-            if (j >= win_lo) full_mask |= 1u << (j - win_lo); else deep_full = true;
+            for (int w = 0; w < W / 2; w++) q.nm[w] = (q.nm[w] >> 1) | (w + 1 < W / 2 ? (q.nm[w + 1 < W / 2 ? w + 1 : w] << 63) : 0ull);
+            if (j <= n) {
+                u32 Eq = c == 0 ? pe0 : c == 1 ? pe1 : c == 2 ? pe2 : pe3;
+                if (isn) Eq = 0;
+                const u32 Xv = Eq | Mv;
+                const u32 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                u32 Ph = Mv | ~(Xh | Pv);
+                u32 Mh = Pv & Xh;
+                score += (int)((Ph >> (m - 1)) & 1u) - (int)((Mh >> (m - 1)) & 1u);
+                Ph <<= 1; Mh <<= 1;
+                Pv = Mh | ~(Xv | Ph);
+                Mv = Ph & Xv;
+                if (j >= win_lo) ring[(j & (K1_RING - 1)) * K1_THREADS] = (u64)Pv | ((u64)Mv << 32);
+                if (score == 0 && exact_j < 0) exact_j = j;          // str.find: leftmost exact occurrence
+                if (score <= thr_m) {
+                    if (j >= win_lo) full_mask |= 1u << (j - win_lo);
+                    else slow = true;      // inexact full-length occurrence far from the read end: literal DP decides
+                }
+            }
         }
     }
-    if (deep_full) return K1_SLOW;     // an inexact full-length occurrence far from the read end: literal DP decides
     // cutadapt keeps the candidate with most matches, then lowest cost, then first
     // visited: full-length candidates by ascending end column, then adapter
     // prefixes i = m .. 0 ending at the read's end.
-    int best_m = 0, best_c = m + n, best_o = K1_NOMATCH, best_v = 0x7fffffff;
     u64 valid = 0;
     {
         int c = 0;
         for (int i = 1; i <= m; i++) {
             c += (int)((Pv >> (i - 1)) & 1u) - (int)((Mv >> (i - 1)) & 1u);
-            if (c <= thr.v[i]) valid |= 1ull << i;
+            if (c <= thr[i]) valid |= 1ull << i;
         }
+        if (n >= win_lo && n >= 1 && ((full_mask >> (n - win_lo)) & 1u)) valid &= ~(1ull << m);   // same cell as the full candidate at column n
     }
-    for (;;) {
-        int i, j, visit;
-        if (full_mask) {
-            const int t = __ffs(full_mask) - 1;
-            full_mask &= full_mask - 1;
-            i = m; j = win_lo + t; visit = j;
-        } else if (valid) {
-            i = 63 - __clzll(valid);
-            valid &= ~(1ull << i);
-            if (i < best_m) break;                      // matches <= i: cannot win any more
-            j = n; visit = n + 1 + (m - i);
-        } else {
-            break;
-        }
-        const int c = k1_cell_cost(ring, i, j);
-        if (j == n && i == best_m && c >= best_c) continue;   // could at best tie, and was visited later
-        int mt, o;
-        if (c == 0) {
-            mt = i; o = j - i;
-        } else {
-            // walk cutadapt's predecessor choice back to a zero-cost (exact) cell
-            int ci = i, cj = j, cc = c;
-            mt = 0; o = -1;
-            for (;;) {
-                if (ci == 0) { o = cj; break; }
-                if (cc == 0) { mt += ci; o = cj - ci; break; }
-                if (cj == 0) { o = 0; break; }
+    int best_m = 0, best_c = m + n, best_o = K1_NOMATCH, best_v = 0x7fffffff;
+    // per-lane state machine: state 0 = fetch next candidate, 1 = walking back, 2 = finished
+    int state = (exact_j >= 0 || slow) ? 2 : 0;
+    int ci = 0, cj = 0, cc = 0, c0 = 0, mt = 0, visit = 0;
+    while (__any_sync(0xffffffffu, state != 2)) {
+        if (state == 0) {
+            int i, j;
+            bool have = true;
+            if (full_mask) {
+                const int t = __ffs(full_mask) - 1;
+                full_mask &= full_mask - 1;
+                i = m; j = win_lo + t; visit = j;
+            } else if (valid) {
+                i = 63 - __clzll(valid);
+                valid &= ~(1ull << i);
+                j = n; visit = n + 1 + (m - i);
+                if (i < best_m) { have = false; state = 2; }          // matches <= i: nothing left can win
+            } else {
+                have = false; state = 2; i = 0; j = 0;
+            }
+            if (have) {
+                const int c = k1_cell_cost(ring, i, j);
+                if (j == n && i == best_m && c >= best_c) {
+                    // could at best tie, and is visited later: skip
+                } else if (c == 0) {
+                    if (i > best_m || (i == best_m && (0 < best_c || visit < best_v))) { best_m = i; best_c = 0; best_o = j - i; best_v = visit; }
+                } else {
+                    ci = i; cj = j; cc = c; c0 = c; mt = 0; state = 1;
+                }
+            }
+        } else if (state == 1) {
+            // one step of cutadapt's predecessor choice, back towards a zero-cost (exact) cell
+            int o = -1;
+            bool done = false;
+            if (ci == 0) { o = cj; done = true; }
+            else if (cc == 0) { mt += ci; o = cj - ci; done = true; }
+            else if (cj == 0) { o = 0; done = true; }
+            else {
                 const int rb = pseq_isn<W>(p, cj - 1) ? 4 : pseq_base<W>(p, cj - 1);
-                const int ab = (int)((tp.aw[a][0] >> ((ci - 1) * 2)) & 3ull);
-                if (rb == ab) { mt++; ci--; cj--; continue; }
-                if (cj < win_lo || (cj - 1 != 0 && cj - 1 < win_lo)) return K1_SLOW;   // needs a column outside the window
-                const int cd = k1_cell_cost(ring, ci - 1, cj - 1) + 1;
-                const int cdel = k1_cell_cost(ring, ci, cj - 1) + 1;
-                const int cins = k1_cell_cost(ring, ci - 1, cj) + 1;
-                if (cd <= cdel && cd <= cins) { ci--; cj--; cc = cd - 1; }
-                else if (cins <= cdel) { ci--; cc = cins - 1; }
-                else { cj--; cc = cdel - 1; }
+                const int ab = (int)((aw >> ((ci - 1) * 2)) & 3ull);
+                if (rb == ab) { mt++; ci--; cj--; }
+                else if (cj < win_lo || (cj - 1 != 0 && cj - 1 < win_lo)) { slow = true; state = 2; }   // needs a column outside the window
+                else {
+                    const int cd = k1_cell_cost(ring, ci - 1, cj - 1) + 1;
+                    const int cdel = k1_cell_cost(ring, ci, cj - 1) + 1;
+                    const int cins = k1_cell_cost(ring, ci - 1, cj) + 1;
+                    if (cd <= cdel && cd <= cins) { ci--; cj--; cc = cd - 1; }
+                    else if (cins <= cdel) { ci--; cc = cins - 1; }
+                    else { cj--; cc = cdel - 1; }
+                }
+            }
+            if (done) {
+                if (mt > best_m || (mt == best_m && (c0 < best_c || (c0 == best_c && visit < best_v)))) {
+                    best_m = mt; best_c = c0; best_o = o; best_v = visit;
+                }
+                state = 0;
             }
         }
-        if (mt > best_m || (mt == best_m && (c < best_c || (c == best_c && visit < best_v)))) {
-            best_m = mt; best_c = c; best_o = o; best_v = visit;
-        }
     }
+    if (exact_j >= 0) { matches_out = m; return exact_j - m; }
+    if (slow) return K1_SLOW;
     matches_out = best_m;
     return best_o;
 }
 
 // AdapterCutter(times=1) over all adapters: most matches wins, first wins ties.
-// Returns the new length, or K1_SLOW.
+// Returns the new length, or K1_SLOW.  Warp-convergent.
 template <int W>
-__device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimParams &tp, const K1Thr &thr, u64 *ring)
+__device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, u64 *ring)
 {
     int best_rstart = -1, best_matches = -1;
+    bool slow = false;
     for (int a = 0; a < tp.n_adapters; a++) {
-        if (tp.alen[a] > 32) return K1_SLOW;
+        if (tp.alen[a] > 32) { slow = true; continue; }
         int mt = 0;
         const int rs = k1_match_fast<W>(p, n, tp, thr, a, ring, mt);
-        if (rs == K1_SLOW) return K1_SLOW;
-        if (rs >= 0 && (best_rstart < 0 || mt > best_matches)) { best_rstart = rs; best_matches = mt; }
+        if (rs == K1_SLOW) slow = true;
+        else if (rs >= 0 && (best_rstart < 0 || mt > best_matches)) { best_rstart = rs; best_matches = mt; }
     }
+    if (slow) return K1_SLOW;
     return best_rstart >= 0 ? best_rstart : n;
 }
 
@@ -216,37 +238,45 @@ __device__ __forceinline__ bool k1_finish(PSeq<W> &p, int n, const TrimParams &t
 template <int W>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-                 u64 n_records, int sample, TrimParams tp, K1Thr thr, TableView<W> T, K1Counters ctr, int force_slow)
+                 u64 n_records, int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, int force_slow)
 {
     __shared__ u64 ring[K1_RING * K1_THREADS];
     __shared__ u32 slowq[K1_QCAP];
     __shared__ u32 slowq_n;
     __shared__ u32 sh_hist[32 * W + 1];
+    __shared__ TrimParams tp;                       // dynamic indexing by adapter: keep it out of local memory
+    __shared__ signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
     for (int b = threadIdx.x; b <= 32 * W; b += K1_THREADS) sh_hist[b] = 0;
+    for (int b = threadIdx.x; b <= MIRGE_MAX_ADAPTER_LEN; b += K1_THREADS) thr[b] = thr_param.v[b];
+    for (int b = threadIdx.x; b < (int)(sizeof(TrimParams) / 4); b += K1_THREADS)
+        reinterpret_cast<u32 *>(&tp)[b] = reinterpret_cast<const u32 *>(&tp_param)[b];
     if (threadIdx.x == 0) slowq_n = 0;
     __syncthreads();
     u32 my_kept = 0, my_slow = 0;
     u64 *my_ring = ring + threadIdx.x;
     for (u64 r0 = (u64)blockIdx.x * K1_THREADS; r0 < n_records; r0 += (u64)gridDim.x * K1_THREADS) {
         const u64 r = r0 + threadIdx.x;
-        if (r < n_records) {
-            PSeq<W> p;
-            int n;
-            k1_load_record<W>(bases, nmask, meta, r, p, n);
-            int nf = n;
-            if (tp.mode == 2) {
-                const int L = tp.uncond;
-                if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); nf = n - cut; }
-                else if (L < 0) { const int cut = (-L) < n ? (-L) : n; nf = n - cut; }
-            } else if (tp.mode == 1) {
-                nf = force_slow ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring);
-            }
-            if (nf == K1_SLOW) {
-                slowq[atomicAdd(&slowq_n, 1u)] = (u32)r;
-            } else {
-                my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
-            }
+        const bool live = r < n_records;
+        PSeq<W> p;
+        int n = 0;
+        if (live) k1_load_record<W>(bases, nmask, meta, r, p, n);
+        else {
+#pragma unroll
+            for (int w = 0; w < W; w++) p.s[w] = 0;
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
         }
+        int nf = n;
+        if (tp.mode == 2) {
+            const int L = tp.uncond;
+            if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); nf = n - cut; }
+            else if (L < 0) { const int cut = (-L) < n ? (-L) : n; nf = n - cut; }
+        } else if (tp.mode == 1) {
+            nf = force_slow ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring);   // warp-uniform branch
+        }
+        __syncwarp();
+        if (live && nf == K1_SLOW) slowq[atomicAdd(&slowq_n, 1u)] = (u32)r;
+        if (live && nf != K1_SLOW) my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
         __syncthreads();
         // drain the slow queue with converged threads once it could overflow on the next
         // tile (every tile adds at most K1_THREADS entries), and after the last tile
@@ -254,11 +284,11 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
         const bool last_tile = r0 + (u64)gridDim.x * K1_THREADS >= n_records;
         if (qn && (qn > K1_QCAP - K1_THREADS || last_tile)) {
             for (u32 q = threadIdx.x; q < qn; q += K1_THREADS) {
-                PSeq<W> p;
-                int n;
-                k1_load_record<W>(bases, nmask, meta, (u64)slowq[q], p, n);
-                const int nf = k1_trim_slow<W>(p, n, tp);
-                my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
+                PSeq<W> ps;
+                int ns;
+                k1_load_record<W>(bases, nmask, meta, (u64)slowq[q], ps, ns);
+                const int nfs = k1_trim_slow<W>(ps, ns, tp);
+                my_kept += k1_finish<W>(ps, nfs, tp, T, sample, sh_hist) ? 1u : 0u;
                 my_slow++;
             }
             __syncthreads();
