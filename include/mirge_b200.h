@@ -145,7 +145,7 @@ uint64_t mirge_hash_sequence(const char *seq, int len);
 /* -- measurement ----------------------------------------------------------- */
 
 /* Per-kernel CUDA-event timing on the context's stream. */
-#define MIRGE_N_KERNELS 16
+#define MIRGE_N_KERNELS 32
 int mirge_profile_enable(mirge_ctx *ctx, int on);
 /* ms[k], launches[k] accumulated since enable; names[k] static strings. */
 int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const char **names);

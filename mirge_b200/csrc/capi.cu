@@ -21,12 +21,17 @@
 #include "k3_tally.cuh"
 
 enum KernelId {
-    KID_K0_COUNT = 0, KID_K0_SCAN, KID_K0_LINES, KID_K0_PACK, KID_K1_TRIM, KID_K2_ROUND, KID_K3_KEYS, KID_K3_SORT,
-    KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_N
+    KID_K0_COUNT = 0, KID_K0_SCAN, KID_K0_LINES, KID_K0_PACK, KID_K1_TRIM, KID_K3_KEYS, KID_K3_SORT,
+    KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_RESET,
+    KID_K2_ROUND0 = 16,   // .. KID_K2_ROUND0 + 9
+    KID_N = 26
 };
 static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
-    "k0_count_newlines", "k0_scan", "k0_line_starts", "k0_pack", "k1_trim_collapse", "k2_round", "k3_make_keys",
-    "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "", ""};
+    "k0_count_newlines", "k0_scan", "k0_line_starts", "k0_pack", "k1_trim_collapse", "k3_make_keys",
+    "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "reset_memset", "", "",
+    "k2_round0_mirna_exact", "k2_round1_hairpin", "k2_round2_mature_trna", "k2_round3_pre_trna", "k2_round4_snorna",
+    "k2_round5_rrna", "k2_round6_ncrna_others", "k2_round7_mrna", "k2_round8_isomir", "k2_round9_spikein",
+    "", "", "", "", "", ""};
 
 struct DevLib {
     u64 *seq = nullptr, *amb = nullptr;
@@ -75,6 +80,7 @@ struct mirge_ctx {
     // tallies
     i64 *d_mir_quant = nullptr, *d_mir_iscan = nullptr, *d_lib_totals = nullptr;
     int tally_nmir = -1;
+    unsigned char *d_tally = nullptr; size_t tally_cap = 0;   // persistent K3 scratch
     bool tallied = false;
     // profiling
     bool prof = false;
@@ -215,7 +221,7 @@ void mirge_destroy(mirge_ctx *ctx)
     cudaFree(ctx->d_round_of); cudaFree(ctx->d_mm_of); cudaFree(ctx->d_ref_of); cudaFree(ctx->d_pos_of);
     cudaFree(ctx->d_ctr); cudaFree(ctx->d_len_hist); cudaFree(ctx->d_todo[0]); cudaFree(ctx->d_todo[1]);
     cudaFree(ctx->d_todo_n); cudaFree(ctx->d_round_stats);
-    cudaFree(ctx->d_mir_quant); cudaFree(ctx->d_mir_iscan); cudaFree(ctx->d_lib_totals);
+    cudaFree(ctx->d_mir_quant); cudaFree(ctx->d_mir_iscan); cudaFree(ctx->d_lib_totals); cudaFree(ctx->d_tally);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -416,7 +422,7 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
     // short as 13 nt (k = 4..8); the big mRNA library gets a 12-mer table.
     std::vector<int> ks;
     if (lib_id == MIRGE_LIB_MIRNA) ks = {4, 5, 6, 7, 8};
-    else if (total > (8u << 20)) ks = {8, 12};
+    else if (total >= (1u << 20)) ks = {8, 12};
     else ks = {8};
     LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.n_refs = n_refs; L.total = (u32)total;
     for (int k : ks) {
@@ -482,7 +488,7 @@ static int annotate_impl(mirge_ctx *ctx)
         for (int t = 0; t < l.ntabs; t++) { R.tabs[t].k = l.tab_k[t]; R.tabs[t].bucket_off = l.tab_off[t]; R.tabs[t].pos = l.tab_pos[t]; }
         const u32 *todo_in = r == 0 ? nullptr : ctx->d_todo[(r - 1) & 1];
         const u64 *n_in = r == 0 ? ctx->d_ctr : ctx->d_todo_n + r;
-        ProfScope ps(ctx, KID_K2_ROUND);
+        ProfScope ps(ctx, KID_K2_ROUND0 + r);
         k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
                                             ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
     }
@@ -517,17 +523,24 @@ int mirge_tally(mirge_ctx *ctx)
         ctx->tally_nmir = n_mir;
     }
     const u32 n_tiles = (u32)((U + RS_TILE - 1) / RS_TILE);
-    u32 *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr}, *hist = nullptr, *scratch = nullptr, *seg_start = nullptr, *seg_end = nullptr;
-    i64 *seg_q = nullptr, *seg_i = nullptr, *seg_u = nullptr;
     const size_t hist_n = (size_t)256 * (n_tiles ? n_tiles : 1);
-    for (int b = 0; b < 2; b++) { CK(cudaMalloc(&keys[b], (U + 1) * sizeof(u32))); CK(cudaMalloc(&vals[b], (U + 1) * sizeof(u32))); }
-    CK(cudaMalloc(&hist, hist_n * sizeof(u32)));
-    CK(cudaMalloc(&scratch, scan_scratch_elems(hist_n) * sizeof(u32)));
-    CK(cudaMalloc(&seg_start, (size_t)n_seg * sizeof(u32)));
-    CK(cudaMalloc(&seg_end, (size_t)n_seg * sizeof(u32)));
-    CK(cudaMalloc(&seg_q, (size_t)n_seg * S * sizeof(i64)));
-    CK(cudaMalloc(&seg_i, (size_t)n_seg * S * sizeof(i64)));
-    CK(cudaMalloc(&seg_u, (size_t)n_seg * S * sizeof(i64)));
+    const size_t max_chunks = (size_t)(U / K3_CHUNK) + n_seg + 1;
+    // one persistent scratch arena, carved into 256-byte aligned pieces
+    size_t need = 0;
+    auto carve = [&need](size_t bytes) { size_t o = need; need += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_keys0 = carve((U + 1) * sizeof(u32)), o_keys1 = carve((U + 1) * sizeof(u32));
+    const size_t o_vals0 = carve((U + 1) * sizeof(u32)), o_vals1 = carve((U + 1) * sizeof(u32));
+    const size_t o_hist = carve(hist_n * sizeof(u32)), o_scr = carve(scan_scratch_elems(hist_n > (size_t)n_seg + 1 ? hist_n : n_seg + 1) * sizeof(u32));
+    const size_t o_ss = carve((size_t)n_seg * sizeof(u32)), o_se = carve((size_t)n_seg * sizeof(u32));
+    const size_t o_ch = carve(((size_t)n_seg + 1) * sizeof(u32));
+    const size_t o_sq = carve((size_t)n_seg * S * sizeof(i64)), o_si = carve((size_t)n_seg * S * sizeof(i64)), o_su = carve((size_t)n_seg * S * sizeof(i64));
+    const size_t o_part = carve(max_chunks * S * 3 * sizeof(i64));
+    CK(ensure(&ctx->d_tally, &ctx->tally_cap, need));
+    unsigned char *tb = ctx->d_tally;
+    u32 *keys[2] = {(u32 *)(tb + o_keys0), (u32 *)(tb + o_keys1)}, *vals[2] = {(u32 *)(tb + o_vals0), (u32 *)(tb + o_vals1)};
+    u32 *hist = (u32 *)(tb + o_hist), *scratch = (u32 *)(tb + o_scr), *seg_start = (u32 *)(tb + o_ss), *seg_end = (u32 *)(tb + o_se);
+    u32 *chunk_off = (u32 *)(tb + o_ch);
+    i64 *seg_q = (i64 *)(tb + o_sq), *seg_i = (i64 *)(tb + o_si), *seg_u = (i64 *)(tb + o_su), *partial = (i64 *)(tb + o_part);
     CK(cudaMemsetAsync(seg_start, 0, (size_t)n_seg * sizeof(u32), st));
     CK(cudaMemsetAsync(seg_end, 0, (size_t)n_seg * sizeof(u32), st));
     const int g = grid_for(U, 256, 148 * 8);
@@ -548,15 +561,15 @@ int mirge_tally(mirge_ctx *ctx)
     }
     { ProfScope ps(ctx, KID_K3_BOUNDS);
       k3_seg_bounds<<<g, 256, 0, st>>>(keys[cur], ctx->d_ctr, seg_start, seg_end); }
-    { ProfScope ps(ctx, KID_K3_REDUCE);
-      k3_seg_reduce<<<grid_for((u64)n_seg * 32, 256, 148 * 8), 256, 0, st>>>(vals[cur], seg_start, seg_end, n_seg, ctx->d_counts,
-                                                                            ctx->d_round_of, S, seg_q, seg_i, seg_u); }
+    { ProfScope ps(ctx, KID_K3_REDUCE, 3);
+      k3_seg_chunks<<<(n_seg + 1 + 255) / 256, 256, 0, st>>>(seg_start, seg_end, n_seg, chunk_off);
+      ctx->n_launches += device_excl_scan(chunk_off, chunk_off, (u64)n_seg + 1, scratch, st);
+      k3_chunk_reduce<<<grid_for((u64)max_chunks * 32, 256, 148 * 8), 256, 0, st>>>(vals[cur], seg_start, seg_end, chunk_off, n_seg,
+                                                                                   ctx->d_counts, ctx->d_round_of, S, partial);
+      k3_seg_reduce<<<grid_for((u64)n_seg * 32, 256, 148 * 8), 256, 0, st>>>(partial, chunk_off, n_seg, S, seg_q, seg_i, seg_u); }
     { ProfScope ps(ctx, KID_K3_FINAL);
       k3_finalize<<<(S + 63) / 64, 64, 0, st>>>(seg_q, seg_i, seg_u, n_mir, S, ctx->d_mir_quant, ctx->d_mir_iscan, ctx->d_lib_totals); }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
-    for (int b = 0; b < 2; b++) { cudaFree(keys[b]); cudaFree(vals[b]); }
-    cudaFree(hist); cudaFree(scratch); cudaFree(seg_start); cudaFree(seg_end); cudaFree(seg_q); cudaFree(seg_i); cudaFree(seg_u);
     ctx->tallied = true;
     return MIRGE_OK;
 }

@@ -135,17 +135,35 @@ k3_seg_bounds(const u32 *__restrict__ keys, const u64 *__restrict__ n_ptr, u32 *
     }
 }
 
-// One warp per segment.  seg_q / seg_i / seg_u are [n_seg][S]:
-// reads, reads from exact-miRNA uniques (round_of == 1), and uniques with a non-zero count.
+// Segments are cut into chunks of K3_CHUNK sorted entries so that the few huge
+// segments (un-annotated, mRNA ...) spread over the whole grid.
+#define K3_CHUNK 1024
+
+// chunks per segment (one thread per segment); n_chunks[n_seg] = 0 so that the
+// exclusive scan leaves the total there.
+__global__ void k3_seg_chunks(const u32 *__restrict__ seg_start, const u32 *__restrict__ seg_end, int n_seg, u32 *__restrict__ n_chunks)
+{
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg < n_seg) n_chunks[seg] = (seg_end[seg] - seg_start[seg] + K3_CHUNK - 1) / K3_CHUNK;
+    else if (seg == n_seg) n_chunks[seg] = 0;
+}
+
+// One warp per chunk: partial[g][s] = {reads, reads of exact-miRNA uniques
+// (round_of == 1), uniques with a non-zero count} over the chunk's entries.
 __global__ void __launch_bounds__(256)
-k3_seg_reduce(const u32 *__restrict__ vals, const u32 *__restrict__ seg_start, const u32 *__restrict__ seg_end, int n_seg,
-              const u32 *__restrict__ counts, const signed char *__restrict__ round_of, int S,
-              i64 *__restrict__ seg_q, i64 *__restrict__ seg_i, i64 *__restrict__ seg_u)
+k3_chunk_reduce(const u32 *__restrict__ vals, const u32 *__restrict__ seg_start, const u32 *__restrict__ seg_end,
+                const u32 *__restrict__ chunk_off, int n_seg, const u32 *__restrict__ counts,
+                const signed char *__restrict__ round_of, int S, i64 *__restrict__ partial)
 {
     const unsigned lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    for (int seg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); seg < n_seg; seg += gridDim.x * warps_per_block) {
-        const u32 a = seg_start[seg], b = seg_end[seg];
+    const u32 total = chunk_off[n_seg];
+    const u32 warps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += warps) {
+        int lo = 0, hi = n_seg;            // segment with chunk_off[seg] <= g < chunk_off[seg + 1]
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (chunk_off[mid] <= g) lo = mid; else hi = mid; }
+        const u32 a = seg_start[lo] + (g - chunk_off[lo]) * K3_CHUNK;
+        const u32 e = seg_end[lo];
+        const u32 b = a + K3_CHUNK < e ? a + K3_CHUNK : e;
         for (int s = 0; s < S; s++) {
             i64 q = 0, qi = 0, qu = 0;
             for (u32 x = a + lane; x < b; x += 32) {
@@ -154,6 +172,32 @@ k3_seg_reduce(const u32 *__restrict__ vals, const u32 *__restrict__ seg_start, c
                 q += c;
                 if (round_of[id] == 1) qi += c;
                 qu += (c != 0);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                q += __shfl_down_sync(0xffffffffu, q, d);
+                qi += __shfl_down_sync(0xffffffffu, qi, d);
+                qu += __shfl_down_sync(0xffffffffu, qu, d);
+            }
+            if (lane == 0) { i64 *o = partial + ((u64)g * S + s) * 3; o[0] = q; o[1] = qi; o[2] = qu; }
+        }
+    }
+}
+
+// One warp per segment sums its chunks' partials.  seg_q / seg_i / seg_u are [n_seg][S].
+__global__ void __launch_bounds__(256)
+k3_seg_reduce(const i64 *__restrict__ partial, const u32 *__restrict__ chunk_off, int n_seg, int S,
+              i64 *__restrict__ seg_q, i64 *__restrict__ seg_i, i64 *__restrict__ seg_u)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int seg = blockIdx.x * warps_per_block + (threadIdx.x >> 5); seg < n_seg; seg += gridDim.x * warps_per_block) {
+        const u32 a = chunk_off[seg], b = chunk_off[seg + 1];
+        for (int s = 0; s < S; s++) {
+            i64 q = 0, qi = 0, qu = 0;
+            for (u32 g = a + lane; g < b; g += 32) {
+                const i64 *o = partial + ((u64)g * S + s) * 3;
+                q += o[0]; qi += o[1]; qu += o[2];
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {

@@ -179,11 +179,11 @@ class Engine:
         self._ck(lib.mirge_profile_enable(self.h, int(on)))
 
     def profile_read(self):
-        ms = np.zeros(16, np.float64)
-        n = np.zeros(16, np.uint64)
-        names = (C.c_char_p * 16)()
+        ms = np.zeros(32, np.float64)
+        n = np.zeros(32, np.uint64)
+        names = (C.c_char_p * 32)()
         self._ck(lib.mirge_profile_read(self.h, _ptr(ms), _ptr(n), C.cast(names, C.c_void_p)))
-        return {names[k].decode(): (float(ms[k]), int(n[k])) for k in range(16) if names[k]}
+        return {names[k].decode(): (float(ms[k]), int(n[k])) for k in range(32) if names[k]}
 
 
 def owner_of(seq, n_parts):
