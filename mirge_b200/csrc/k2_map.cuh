@@ -190,7 +190,27 @@ struct K2Arrays {
     signed char *mm_of;
 };
 
-// One thread per still un-annotated unique sequence.  todo_in == nullptr means
+#define K2_HEAVY 16     // seed buckets at least this long are verified by the whole warp
+
+template <int W>
+__device__ __forceinline__ Query<W> query_bcast(const Query<W> &q, int src)
+{
+    Query<W> r;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        r.s[w] = __shfl_sync(0xffffffffu, q.s[w], src);
+        r.n2[w] = __shfl_sync(0xffffffffu, q.n2[w], src);
+        r.len2[w] = __shfl_sync(0xffffffffu, q.len2[w], src);
+    }
+    r.n = __shfl_sync(0xffffffffu, q.n, src);
+    return r;
+}
+
+// One thread per still un-annotated unique sequence; a warp works through its 32
+// sequences seed by seed.  Short seed buckets are verified by the owning lane;
+// long ones (few-base seeds of the isomiR round, big libraries) are broadcast
+// and verified by all 32 lanes, then min-reduced back to the owner, so one
+// expensive sequence does not serialise its warp.  todo_in == nullptr means
 // the identity list 0 .. *n_in-1.  Sequences that stay un-annotated (filtered
 // out by length, or without a valid placement) are appended to todo_out.
 template <int W>
@@ -202,20 +222,25 @@ k2_round(K2Arrays A, const u32 *__restrict__ todo_in, const u64 *__restrict__ n_
     const u64 n_in = *n_in_ptr;
     const unsigned lane = threadIdx.x & 31;
     u32 my_proc = 0, my_aln = 0;
+    const int nseeds = R.param + 1;
     for (u64 base = (u64)blockIdx.x * blockDim.x; base < n_in; base += (u64)gridDim.x * blockDim.x) {
         const u64 i = base + threadIdx.x;
         const bool active = i < n_in;
         u32 id = 0;
-        bool hit = false;
+        bool pass = false;
+        Query<W> q;
+        q.n = 0;
+#pragma unroll
+        for (int w = 0; w < W; w++) { q.s[w] = 0; q.n2[w] = 0; q.len2[w] = 0; }
         if (active) {
             id = todo_in ? todo_in[i] : (u32)i;
             const int len = A.ulen[id];
-            bool pass = true;
+            pass = L.seq != nullptr;
             if (R.len_filter < 0 && !(len < -R.len_filter)) pass = false;
             if (R.len_filter > 0 && !(len > R.len_filter)) pass = false;
-            PSeq<W> p;
-            int n = 0;
             if (pass) {
+                PSeq<W> p;
+                int n = 0;
 #pragma unroll
                 for (int w = 0; w < W; w++) p.s[w] = A.useq[(u64)id * W + w];
 #pragma unroll
@@ -231,53 +256,82 @@ k2_round(K2Arrays A, const u32 *__restrict__ todo_in, const u64 *__restrict__ n_
                     if (n <= 0) pass = false;
                     else { pseq_shift<W>(p, R.trim5); pseq_truncate<W>(p, n); }
                 }
-            }
-            if (pass && L.seq != nullptr) {
-                my_proc++;
-                Query<W> q;
-                q.n = n;
+                if (pass) {
+                    q.n = n;
 #pragma unroll
-                for (int w = 0; w < W; w++) {
-                    q.s[w] = p.s[w];
-                    q.n2[w] = spread32((u32)(p.nm[w >> 1] >> ((w & 1) * 32)));
-                    const int lo = w * 32;
-                    q.len2[w] = (n <= lo) ? 0ull : (n >= lo + 32) ? 0x5555555555555555ull
-                                                                   : (0x5555555555555555ull & ((1ull << ((n - lo) * 2)) - 1ull));
-                }
-                const int region = (R.mode == 0) ? (n < 28 ? n : 28) : n;
-                const int nseeds = R.param + 1;
-                const int maxk = region / nseeds;
-                int ti = -1;
-                for (int t = 0; t < R.ntabs; t++) if (R.tabs[t].k <= maxk) ti = t;
-                u64 best = ~0ull;
-                if (ti < 0) {
-                    // no seed table short enough (only with a non-default min_length): scan every offset
-                    for (u64 g = 0; g + (u64)n <= (u64)L.total; g++) consider<W>(L, q, (u32)g, R, best);
-                } else {
-                    const KmerTab T = R.tabs[ti];
-                    const u64 kmask = (T.k == 32) ? ~0ull : ((1ull << (2 * T.k)) - 1ull);
-                    for (int sd = 0; sd < nseeds; sd++) {
-                        const int so = sd * T.k;
-                        if (words_window64<W>(q.n2, so) & kmask) continue;   // a seed holding N cannot match exactly
-                        const u32 code = (u32)(words_window64<W>(q.s, so) & kmask);
-                        const u32 lo = __ldg(T.bucket_off + code), hi = __ldg(T.bucket_off + code + 1);
-                        for (u32 x = lo; x < hi; x++) {
-                            const u32 ppos = __ldg(T.pos + x);
-                            if (ppos >= (u32)so) consider<W>(L, q, ppos - (u32)so, R, best);
-                        }
+                    for (int w = 0; w < W; w++) {
+                        q.s[w] = p.s[w];
+                        q.n2[w] = spread32((u32)(p.nm[w >> 1] >> ((w & 1) * 32)));
+                        const int lo = w * 32;
+                        q.len2[w] = (n <= lo) ? 0ull : (n >= lo + 32) ? 0x5555555555555555ull
+                                                                       : (0x5555555555555555ull & ((1ull << ((n - lo) * 2)) - 1ull));
                     }
                 }
-                if (best != ~0ull) {
-                    hit = true;
-                    const u32 g = R.highest ? ~(u32)best : (u32)best;
-                    const int r = ref_of_gpos(L, g);
-                    A.round_of[id] = (signed char)(R.round + 1);
-                    A.ref_of[id] = r;
-                    A.pos_of[id] = (int)(g - __ldg(L.ref_off + r));
-                    A.mm_of[id] = (signed char)(best >> 32);
-                    my_aln++;
+            }
+        }
+        u64 best = ~0ull;
+        int ti = -1;
+        if (pass) {
+            my_proc++;
+            const int region = (R.mode == 0) ? (q.n < 28 ? q.n : 28) : q.n;
+            const int maxk = region / nseeds;
+            for (int t = 0; t < R.ntabs; t++) if (R.tabs[t].k <= maxk) ti = t;
+            if (ti < 0) {
+                // no seed table short enough (only with a non-default min_length): scan every offset
+                for (u64 g = 0; g + (u64)q.n <= (u64)L.total; g++) consider<W>(L, q, (u32)g, R, best);
+            }
+        }
+        for (int sd = 0; sd < nseeds; sd++) {           // warp-uniform trip count
+            u32 lo = 0, hi = 0;
+            int so = 0;
+            if (pass && ti >= 0) {
+                const KmerTab T = R.tabs[ti];
+                const u64 kmask = (T.k == 32) ? ~0ull : ((1ull << (2 * T.k)) - 1ull);
+                so = sd * T.k;
+                if (!(words_window64<W>(q.n2, so) & kmask)) {   // a seed holding N cannot match exactly
+                    const u32 code = (u32)(words_window64<W>(q.s, so) & kmask);
+                    lo = __ldg(T.bucket_off + code); hi = __ldg(T.bucket_off + code + 1);
                 }
             }
+            const u32 cnt = hi - lo;
+            if (cnt && cnt < K2_HEAVY) {
+                const KmerTab T = R.tabs[ti];
+                for (u32 x = lo; x < hi; x++) {
+                    const u32 ppos = __ldg(T.pos + x);
+                    if (ppos >= (u32)so) consider<W>(L, q, ppos - (u32)so, R, best);
+                }
+            }
+            unsigned heavy = __ballot_sync(0xffffffffu, cnt >= K2_HEAVY);
+            while (heavy) {
+                const int src = __ffs(heavy) - 1;
+                heavy &= heavy - 1;
+                const Query<W> qb = query_bcast<W>(q, src);
+                const u32 blo = __shfl_sync(0xffffffffu, lo, src), bhi = __shfl_sync(0xffffffffu, hi, src);
+                const int bso = __shfl_sync(0xffffffffu, so, src), bti = __shfl_sync(0xffffffffu, ti, src);
+                const u32 *pos = R.tabs[bti].pos;
+                u64 lb = ~0ull;
+                for (u32 x = blo + lane; x < bhi; x += 32) {
+                    const u32 ppos = __ldg(pos + x);
+                    if (ppos >= (u32)bso) consider<W>(L, qb, ppos - (u32)bso, R, lb);
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const u64 o = __shfl_xor_sync(0xffffffffu, lb, d);
+                    lb = o < lb ? o : lb;
+                }
+                if ((int)lane == src && lb < best) best = lb;
+            }
+        }
+        bool hit = false;
+        if (pass && best != ~0ull) {
+            hit = true;
+            const u32 g = R.highest ? ~(u32)best : (u32)best;
+            const int r = ref_of_gpos(L, g);
+            A.round_of[id] = (signed char)(R.round + 1);
+            A.ref_of[id] = r;
+            A.pos_of[id] = (int)(g - __ldg(L.ref_off + r));
+            A.mm_of[id] = (signed char)(best >> 32);
+            my_aln++;
         }
         const bool push = active && !hit;
         const unsigned bal = __ballot_sync(0xffffffffu, push);
