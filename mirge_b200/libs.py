@@ -1,0 +1,77 @@
+"""Library directory of `miRge2.0 annotate` (src/mirge/__main__.py:110-112,262-281).
+
+    <lib>/<species>/index.Libs/<sp>_{mirna_<DB>,hairpin_<DB>,mrna,mature_trna,pre_trna,
+                                    snorna,rrna,ncrna_others,spike-in}.*.ebwt
+    <lib>/<species>/fasta.Libs/<sp>_mirna_SNP_pseudo_<DB>.fa
+    <lib>/<species>/annotation.Libs/<sp>_merges_<DB>.csv
+
+The reference hands the `.ebwt` indexes to bowtie.  The CUDA mapper needs the
+reference sequences themselves, so next to every index it expects
+`<index>.fa` -- exactly what `bowtie-inspect <index> > <index>.fa` prints
+(the reference itself calls bowtie-inspect at utils/summarize.py:6 and
+utils/runAnnotationPipeline.py:610-611).  The presence check on `.1.ebwt`
+(:262-267) and its message are kept.
+"""
+import os
+
+LIB_TYPES = {            # library slot -> index basename suffix
+    'mirna': 'mirna_%(db)s', 'hairpin': 'hairpin_%(db)s', 'mrna': 'mrna', 'mature_trna': 'mature_trna',
+    'pre_trna': 'pre_trna', 'snorna': 'snorna', 'rrna': 'rrna', 'ncrna_others': 'ncrna_others', 'spike-in': 'spike-in',
+}
+REQUIRED = ['mirna', 'hairpin', 'mrna', 'mature_trna', 'pre_trna', 'snorna', 'rrna', 'ncrna_others']   # :262
+
+
+class LibraryError(Exception):
+    pass
+
+
+def read_fasta(path):
+    """FASTA -> (names, seqs); a name is the header up to the first whitespace
+    (what bowtie reports as RNAME and bowtie-inspect -n lists)."""
+    names, seqs, cur = [], [], []
+    with open(path) as f:
+        for line in f:
+            if line.startswith('>'):
+                if names:
+                    seqs.append(''.join(cur))
+                hdr = line[1:].strip()
+                names.append(hdr.split()[0] if hdr else '')
+                cur = []
+            else:
+                cur.append(line.strip())
+    if names:
+        seqs.append(''.join(cur))
+    return names, seqs
+
+
+class LibraryDir:
+    def __init__(self, library_path, species, db, spike_in=False):
+        self.species, self.db = species, db
+        self.index_path = os.path.join(library_path, species, 'index.Libs')
+        self.mirna_fa = os.path.join(library_path, species, 'fasta.Libs', '%s_mirna_SNP_pseudo_%s.fa' % (species, db))
+        self.merges_csv = os.path.join(library_path, species, 'annotation.Libs', '%s_merges_%s.csv' % (species, db))
+        self.types = list(REQUIRED) + (['spike-in'] if spike_in else [])
+
+    def index_base(self, t):
+        return os.path.join(self.index_path, '%s_%s' % (self.species, LIB_TYPES[t] % {'db': self.db}))
+
+    def check(self):
+        """The reference's index presence check (__main__.py:262-267), same message."""
+        for t in REQUIRED:
+            if not os.path.isfile(self.index_base(t) + '.1.ebwt'):
+                raise LibraryError('The bowtie index file of %s_%s.*.ebwt is not located at %s, please check it.'
+                                   % (self.species, LIB_TYPES[t] % {'db': self.db}, self.index_path))
+
+    def load(self, t):
+        fa = self.index_base(t) + '.fa'
+        if not os.path.isfile(fa):
+            raise LibraryError('%s is missing: the CUDA mapper reads reference sequences from a FASTA next to each bowtie '
+                               'index; create it with `bowtie-inspect %s > %s`.' % (fa, self.index_base(t), fa))
+        return read_fasta(fa)
+
+    def merge_lines(self):
+        """Rows of <sp>_merges_<DB>.csv; a missing file skips the merge (miRNAmerge.py:13,42-43)."""
+        if not os.path.isfile(self.merges_csv):
+            return None
+        with open(self.merges_csv) as f:
+            return [line for line in f if line.strip()]
