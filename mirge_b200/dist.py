@@ -53,5 +53,5 @@ def hash_partition(engine, stream=None, group=None):
     torch.cuda.current_stream().synchronize()
     engine.reset_unique()
     engine.import_records_device(recv.data_ptr(), n_recv)
-    engine.sync()
-    return n_recv
+    _, _, n_owned = engine.stats()      # records of one sequence from several ranks merge here
+    return n_owned
