@@ -50,6 +50,9 @@ struct mirge_ctx {
     int device = 0, S = 1, spike_in = 0, W = 2, max_len = 64;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;             // H2D copies of mirge_feed_fastq
+    std::vector<cudaEvent_t> copy_events;
+    u32 *d_carry = nullptr;                         // line starts carried across feed regions
     std::string err;
     // trim configuration
     TrimParams tp;
@@ -190,6 +193,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_todo[0], max_unique * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_todo[1], max_unique * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 1) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_carry, 16 * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_round_stats, 2 * MIRGE_N_ROUNDS * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_lib_totals, (size_t)n_samples * MIRGE_N_TOTALS * sizeof(i64)));
     CK(cudaMemsetAsync(ctx->d_slots, 0, cap * esz, ctx->stream));
@@ -222,6 +226,9 @@ void mirge_destroy(mirge_ctx *ctx)
     cudaFree(ctx->d_ctr); cudaFree(ctx->d_len_hist); cudaFree(ctx->d_todo[0]); cudaFree(ctx->d_todo[1]);
     cudaFree(ctx->d_todo_n); cudaFree(ctx->d_round_stats);
     cudaFree(ctx->d_mir_quant); cudaFree(ctx->d_mir_iscan); cudaFree(ctx->d_lib_totals); cudaFree(ctx->d_tally);
+    for (auto e : ctx->copy_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    cudaFree(ctx->d_carry);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -302,49 +309,104 @@ int mirge_detect_phred(const char *buf, uint64_t n)
 
 __global__ void k_set_u32(u32 *p, u32 v) { *p = v; }
 
+#define FEED_REGION_BYTES (64ull << 20)
+
+// Core of mirge_feed_fastq{,_device}: the chunk is consumed region by region.
+// With a host source every region's H2D copy is queued up front on the copy
+// stream, and K0/K1 of region r run on the compute stream as soon as copy r has
+// landed, so transfers overlap the kernels.  Line starts are carried across
+// regions (a record may straddle a boundary): d_lines = [q pending complete
+// lines + current partial line | line starts found in this region].
 template <int W>
-static int feed_device_impl(mirge_ctx *ctx, int sample, const unsigned char *d_text, uint64_t nbytes, int phred_base, int last_char)
+static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint64_t nbytes, int phred_base,
+                        const char *host_src, int last_char)
 {
     cudaStream_t st = ctx->stream;
-    const u64 ntiles = (nbytes + K0_TILE_BYTES - 1) / K0_TILE_BYTES;
-    CK(ensure(&ctx->d_tile, &ctx->tile_cap, ntiles + 2));
-    CK(ensure(&ctx->d_scan, &ctx->scan_cap, scan_scratch_elems(ntiles + 1)));
-    const uint4 *t16 = reinterpret_cast<const uint4 *>(d_text);
-    { ProfScope ps(ctx, KID_K0_COUNT);
-      CK(cudaMemsetAsync(ctx->d_tile + ntiles, 0, sizeof(u32), st));
-      k0_count_newlines<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, nbytes, ctx->d_tile); }
-    { ProfScope ps(ctx, KID_K0_SCAN, 0);
-      ctx->n_launches += device_excl_scan(ctx->d_tile, ctx->d_tile, ntiles + 1, ctx->d_scan, st); }
-    u32 n_newlines = 0;
-    CK(cudaMemcpyAsync(&n_newlines, ctx->d_tile + ntiles, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const u64 n_lines = (u64)n_newlines + (last_char != '\n' ? 1 : 0);
-    if (n_lines % 4 != 0) return fail(ctx, MIRGE_E_FORMAT, "FASTQ chunk does not hold a whole number of 4-line records");
-    const u64 nrec = n_lines / 4;
-    CK(ensure(&ctx->d_lines, &ctx->lines_cap, n_lines + 2));
-    if (nrec > ctx->rec_cap) {
-        cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
-        ctx->d_bases = ctx->d_nmask = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
-        const size_t cap = nrec + nrec / 8 + 64;
-        CK(cudaMalloc(&ctx->d_bases, cap * W * sizeof(u64)));
-        CK(cudaMalloc(&ctx->d_nmask, cap * (W / 2) * sizeof(u64)));
-        CK(cudaMalloc(&ctx->d_meta, cap * sizeof(u32)));
-        ctx->rec_cap = cap;
+    const u64 region = host_src ? FEED_REGION_BYTES : nbytes;
+    const int nreg = (int)((nbytes + region - 1) / region);
+    if (host_src) {
+        if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        while ((int)ctx->copy_events.size() < nreg + 1) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->copy_events.push_back(e);
+        }
+        // earlier kernels may still read d_text
+        CK(cudaEventRecord(ctx->copy_events[nreg], st));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[nreg], 0));
+        cudaEvent_t pa = nullptr, pb = nullptr;
+        if (ctx->prof) { cudaEventCreate(&pa); cudaEventCreate(&pb); cudaEventRecord(pa, ctx->copy_stream); }
+        for (int r = 0; r < nreg; r++) {
+            const u64 a = (u64)r * region, len = (a + region <= nbytes) ? region : nbytes - a;
+            CK(cudaMemcpyAsync(d_text + a, host_src + a, len, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->copy_events[r], ctx->copy_stream));
+        }
+        if (ctx->prof) { cudaEventRecord(pb, ctx->copy_stream); ctx->spans.push_back({KID_H2D, pa, pb}); }
     }
-    { ProfScope ps(ctx, KID_K0_LINES);
-      CK(cudaMemsetAsync(ctx->d_lines, 0, sizeof(u32), st));
-      k0_line_starts<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, nbytes, ctx->d_tile, ctx->d_lines);
-      if (last_char != '\n') { k_set_u32<<<1, 1, 0, st>>>(ctx->d_lines + n_lines, (u32)(nbytes + 1)); ctx->n_launches++; } }
     K0Params kp; kp.phred_base = phred_base; kp.qual_cutoff = ctx->qual_cutoff; kp.max_len = ctx->max_len;
-    { ProfScope ps(ctx, KID_K0_PACK);
-      k0_pack<W><<<grid_for(nrec, 256, 148 * 16), 256, 0, st>>>(d_text, ctx->d_lines, nrec, kp, ctx->d_bases, ctx->d_nmask,
-                                                               ctx->d_meta, (u32 *)(ctx->d_ctr + 1)); }
     K1Counters kc; kc.kept = ctx->d_ctr + 2; kc.len_hist = ctx->d_len_hist; kc.slow_reads = ctx->d_ctr + 2 + ctx->S;
-    { ProfScope ps(ctx, KID_K1_TRIM);
-      k1_trim_collapse<W><<<grid_for(nrec, 128, 148 * 16), 128, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample,
-                                                                        ctx->tp, ctx->thr, table_view<W>(ctx), kc, ctx->force_slow); }
+    CK(ensure(&ctx->d_lines, &ctx->lines_cap, 64));
+    CK(cudaMemsetAsync(ctx->d_lines, 0, sizeof(u32), st));       // the first line starts at offset 0
+    u32 q = 0;                                                   // complete lines pending since the last record boundary
+    for (int r = 0; r < nreg; r++) {
+        const u64 a = (u64)r * region, len = (a + region <= nbytes) ? region : nbytes - a;
+        if (host_src) CK(cudaStreamWaitEvent(st, ctx->copy_events[r], 0));
+        const u64 ntiles = (len + K0_TILE_BYTES - 1) / K0_TILE_BYTES;
+        CK(ensure(&ctx->d_tile, &ctx->tile_cap, ntiles + 2));
+        CK(ensure(&ctx->d_scan, &ctx->scan_cap, scan_scratch_elems(ntiles + 1)));
+        const uint4 *t16 = reinterpret_cast<const uint4 *>(d_text + a);
+        { ProfScope ps(ctx, KID_K0_COUNT);
+          CK(cudaMemsetAsync(ctx->d_tile + ntiles, 0, sizeof(u32), st));
+          k0_count_newlines<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, len, ctx->d_tile); }
+        { ProfScope ps(ctx, KID_K0_SCAN, 0);
+          ctx->n_launches += device_excl_scan(ctx->d_tile, ctx->d_tile, ntiles + 1, ctx->d_scan, st); }
+        u32 c = 0;
+        CK(cudaMemcpyAsync(&c, ctx->d_tile + ntiles, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const bool last = r == nreg - 1;
+        const u32 extra = (last && last_char != '\n') ? 1u : 0u;  // unterminated final line
+        const u64 lines = (u64)q + c + extra;
+        if (last && lines % 4 != 0) return fail(ctx, MIRGE_E_FORMAT, "FASTQ chunk does not hold a whole number of 4-line records");
+        const u64 nrec = lines / 4;
+        if (ctx->lines_cap < lines + 8) {                         // grow, keeping the carried line starts
+            u32 *nl = nullptr;
+            const size_t cap = lines + lines / 8 + 64;
+            CK(cudaMalloc(&nl, cap * sizeof(u32)));
+            CK(cudaMemcpyAsync(nl, ctx->d_lines, (size_t)(q + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            cudaFree(ctx->d_lines);
+            ctx->d_lines = nl; ctx->lines_cap = cap;
+        }
+        { ProfScope ps(ctx, KID_K0_LINES);
+          k0_line_starts<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, len, ctx->d_tile, ctx->d_lines, q + 1, a);
+          if (extra) { k_set_u32<<<1, 1, 0, st>>>(ctx->d_lines + q + 1 + c, (u32)(nbytes + 1)); ctx->n_launches++; } }
+        if (nrec) {
+            if (nrec > ctx->rec_cap) {
+                cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
+                ctx->d_bases = ctx->d_nmask = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
+                const size_t cap = nrec + nrec / 8 + 64;
+                CK(cudaMalloc(&ctx->d_bases, cap * W * sizeof(u64)));
+                CK(cudaMalloc(&ctx->d_nmask, cap * (W / 2) * sizeof(u64)));
+                CK(cudaMalloc(&ctx->d_meta, cap * sizeof(u32)));
+                ctx->rec_cap = cap;
+            }
+            { ProfScope ps(ctx, KID_K0_PACK);
+              k0_pack<W><<<grid_for(nrec, 256, 148 * 16), 256, 0, st>>>(d_text, ctx->d_lines, nrec, kp, ctx->d_bases, ctx->d_nmask,
+                                                                       ctx->d_meta, (u32 *)(ctx->d_ctr + 1)); }
+            { ProfScope ps(ctx, KID_K1_TRIM);
+              k1_trim_collapse<W><<<grid_for(nrec, K1_THREADS, 148 * 16), K1_THREADS, 0, st>>>(
+                  ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->thr, table_view<W>(ctx), kc, ctx->force_slow); }
+        }
+        // carry the pending line starts to the front for the next region
+        const u32 q2 = (u32)(lines % 4);
+        if (!last && nrec) {
+            CK(cudaMemcpyAsync(ctx->d_carry, ctx->d_lines + 4 * nrec, (size_t)(q2 + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(ctx->d_lines, ctx->d_carry, (size_t)(q2 + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        }
+        q = q2;
+        ctx->processed[sample] += nrec;
+    }
     CK(cudaGetLastError());
-    ctx->processed[sample] += nrec;
     ctx->annotated = false; ctx->tallied = false;
     return MIRGE_OK;
 }
@@ -357,8 +419,9 @@ int mirge_feed_fastq_device(mirge_ctx *ctx, int sample, const void *fastq_dev, u
     unsigned char last = 0;
     CK(cudaMemcpyAsync(&last, (const unsigned char *)fastq_dev + nbytes - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    return ctx->W == 2 ? feed_device_impl<2>(ctx, sample, (const unsigned char *)fastq_dev, nbytes, phred_base, last)
-                       : feed_device_impl<4>(ctx, sample, (const unsigned char *)fastq_dev, nbytes, phred_base, last);
+    unsigned char *t = (unsigned char *)const_cast<void *>(fastq_dev);
+    return ctx->W == 2 ? feed_regions<2>(ctx, sample, t, nbytes, phred_base, nullptr, last)
+                       : feed_regions<4>(ctx, sample, t, nbytes, phred_base, nullptr, last);
 }
 
 int mirge_feed_fastq(mirge_ctx *ctx, int sample, const char *fastq, uint64_t nbytes, int phred_base)
@@ -366,12 +429,13 @@ int mirge_feed_fastq(mirge_ctx *ctx, int sample, const char *fastq, uint64_t nby
     if (sample < 0 || sample >= ctx->S || !fastq || nbytes >= 0xFFFFFFF0ull) return fail(ctx, MIRGE_E_ARG, "mirge_feed_fastq: bad argument (chunk must be < 4 GiB)");
     if (nbytes == 0) return MIRGE_OK;
     CK(cudaSetDevice(ctx->device));
-    CK(ensure(&ctx->d_text, &ctx->text_cap, (size_t)nbytes + 64));
-    { ProfScope ps(ctx, KID_H2D, 0);
-      CK(cudaMemcpyAsync(ctx->d_text, fastq, nbytes, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (ctx->text_cap < (size_t)nbytes + 64) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(ensure(&ctx->d_text, &ctx->text_cap, (size_t)nbytes + 64));
+    }
     const int last = (unsigned char)fastq[nbytes - 1];
-    return ctx->W == 2 ? feed_device_impl<2>(ctx, sample, ctx->d_text, nbytes, phred_base, last)
-                       : feed_device_impl<4>(ctx, sample, ctx->d_text, nbytes, phred_base, last);
+    return ctx->W == 2 ? feed_regions<2>(ctx, sample, ctx->d_text, nbytes, phred_base, fastq, last)
+                       : feed_regions<4>(ctx, sample, ctx->d_text, nbytes, phred_base, fastq, last);
 }
 
 int mirge_get_stats(mirge_ctx *ctx, uint64_t *processed, uint64_t *kept, uint64_t *n_unique)

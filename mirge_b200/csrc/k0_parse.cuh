@@ -50,25 +50,26 @@ k0_count_newlines(const uint4 *__restrict__ text16, u64 nbytes, u32 *__restrict_
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
 }
 
-// tile_offsets = exclusive scan of tile_counts.  line_start[0] = 0 is written by
-// the host-side launcher; line k+1 starts one past the k-th newline.
+// tile_offsets = exclusive scan of tile_counts.  The k-th newline of this region
+// (0-based) puts the start of the following line into line_start[idx_base + k];
+// offsets are relative to the whole chunk (byte_base = offset of this region).
 __global__ void __launch_bounds__(K0_THREADS)
 k0_line_starts(const uint4 *__restrict__ text16, u64 nbytes, const u32 *__restrict__ tile_offsets,
-               u32 *__restrict__ line_start)
+               u32 *__restrict__ line_start, u32 idx_base, u64 byte_base)
 {
     __shared__ u32 sh[33];
     u64 unit0 = (u64)blockIdx.x * (K0_THREADS * K0_STEPS);
-    u32 base = tile_offsets[blockIdx.x];
+    u32 base = tile_offsets[blockIdx.x] + idx_base;
     for (int s = 0; s < K0_STEPS; s++) {
         u64 u = unit0 + (u64)s * K0_THREADS + threadIdx.x;
         u32 m = nl_mask16(text16, u, nbytes);
         u32 total;
         u32 pre = block_excl_scan(__popc(m), sh, &total);
-        u32 idx = base + pre + 1;
+        u32 idx = base + pre;
         while (m) {
             int b = __ffs(m) - 1;
             m &= m - 1;
-            line_start[idx++] = (u32)(u * 16ull + b + 1);
+            line_start[idx++] = (u32)(byte_base + u * 16ull + b + 1);
         }
         base += total;
     }

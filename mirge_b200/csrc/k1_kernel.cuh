@@ -23,7 +23,7 @@
 #include "k1_trim.cuh"
 
 #define K1_THREADS 128
-#define K1_RING 8
+#define K1_RING 16
 #define K1_QCAP (3 * K1_THREADS)
 
 struct K1Counters {
@@ -70,49 +70,63 @@ __device__ __forceinline__ int k1_cell_cost(const u64 *ring, int i, int j)
 // Fast adapter search for one adapter of length m <= 32, executed by all 32
 // lanes of a warp in lock step (every loop has a warp-uniform trip count, so
 // lanes never serialise behind each other's data-dependent work).
+//
+// Per column j the ring keeps (Pv_j, Mv_j) -- vertical cost deltas, from which any
+// cell cost is two popcounts -- and MhS_j, the shifted negative horizontal deltas.
+// cutadapt's choice at a mismatching cell (i, j) follows from those bits alone:
+//   cost_diag <= cost_ins  <=>  cost(i-1,j-1) <= cost(i-1,j)  <=>  bit i-1 of MhS_j clear
+//   cost_diag <= cost_del  <=>  cost(i-1,j-1) <= cost(i,j-1)  <=>  bit i-1 of Mv_{j-1} clear
+// and when the diagonal loses, insertion wins iff the MhS_j bit is set
+// (cost_ins <= cost_del  <=>  hdelta <= vdelta, with one of them -1).
 // Returns rstart >= 0 (matches in matches_out), K1_NOMATCH, or K1_SLOW.
-// `ring` points at this thread's column slot 0 (stride K1_THREADS between slots).
+// `ring`/`ringh` point at this thread's slot 0 (stride K1_THREADS between slots).
 template <int W>
 __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, int a,
-                                             u64 *ring, int &matches_out)
+                                             u64 *ring, u32 *ringh, const u32 *peq8, int &matches_out)
 {
+    // peq8[c | isN << 2]: match mask of read base c against the adapter (0 for N)
     const int m = tp.alen[a];
-    const u64 aw = tp.aw[a][0];
-    const u32 pe0 = (u32)tp.peq[a][0], pe1 = (u32)tp.peq[a][1], pe2 = (u32)tp.peq[a][2], pe3 = (u32)tp.peq[a][3];
     u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
     int score = m;
     const int thr_m = thr[m];
     const int win_lo = n - (K1_RING - 1);          // first column kept in the ring
+    const int top = m - 1;
     u32 full_mask = 0;                             // bit (j - win_lo): inexact full-length candidate ending at column j
     bool slow = false;
     int exact_j = -1;
     const int nmax = __reduce_max_sync(0xffffffffu, n);
-    {
-        PSeq<W> q = p;                             // consumed base by base
-        for (int j = 1; j <= nmax; j++) {
-            const u32 c = (u32)(q.s[0] & 3ull);
-            const bool isn = (q.nm[0] & 1ull) != 0;
+    for (int j0 = 0; j0 < nmax; j0 += 16) {        // 16 bases (one 32-bit word) per outer step
+        u32 bw = 0, nb = 0;
 #pragma unroll
-            for (int w = 0; w < W; w++) q.s[w] = (q.s[w] >> 2) | (w + 1 < W ? (q.s[w + 1 < W ? w + 1 : w] << 62) : 0ull);
-#pragma unroll
-            for (int w = 0; w < W / 2; w++) q.nm[w] = (q.nm[w] >> 1) | (w + 1 < W / 2 ? (q.nm[w + 1 < W / 2 ? w + 1 : w] << 63) : 0ull);
+        for (int w = 0; w < W; w++) {
+            if ((j0 >> 5) == w) {
+                bw = (u32)(p.s[w] >> ((j0 & 16) * 2));
+                nb = (u32)(p.nm[w >> 1] >> (((w & 1) * 32) + (j0 & 16))) & 0xFFFFu;
+            }
+        }
+        const int jend = (nmax - j0) < 16 ? (nmax - j0) : 16;
+        for (int t = 0; t < jend; t++) {
+            const int j = j0 + t + 1;
+            const u32 Eq = peq8[(bw & 3u) | (((nb >> t) & 1u) << 2)];
+            bw >>= 2;
             if (j <= n) {
-                u32 Eq = c == 0 ? pe0 : c == 1 ? pe1 : c == 2 ? pe2 : pe3;
-                if (isn) Eq = 0;
                 const u32 Xv = Eq | Mv;
                 const u32 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
                 u32 Ph = Mv | ~(Xh | Pv);
                 u32 Mh = Pv & Xh;
-                score += (int)((Ph >> (m - 1)) & 1u) - (int)((Mh >> (m - 1)) & 1u);
+                score += (int)((Ph >> top) & 1u) - (int)((Mh >> top) & 1u);
                 Ph <<= 1; Mh <<= 1;
                 Pv = Mh | ~(Xv | Ph);
                 Mv = Ph & Xv;
-                if (j >= win_lo) ring[(j & (K1_RING - 1)) * K1_THREADS] = (u64)Pv | ((u64)Mv << 32);
-                if (score == 0 && exact_j < 0) exact_j = j;          // str.find: leftmost exact occurrence
-                if (score <= thr_m) {
-                    if (j >= win_lo) full_mask |= 1u << (j - win_lo);
-                    else slow = true;      // inexact full-length occurrence far from the read end: literal DP decides
+                if (j >= win_lo) {
+                    const int slot = (j & (K1_RING - 1)) * K1_THREADS;
+                    ring[slot] = (u64)Pv | ((u64)Mv << 32);
+                    ringh[slot] = Mh;
+                    if (score <= thr_m) full_mask |= 1u << (j - win_lo);
+                } else if (score <= thr_m) {
+                    slow = true;           // inexact full-length occurrence far from the read end: literal DP decides
                 }
+                if (score == 0 && exact_j < 0) exact_j = j;          // str.find: leftmost exact occurrence
             }
         }
     }
@@ -126,7 +140,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
             c += (int)((Pv >> (i - 1)) & 1u) - (int)((Mv >> (i - 1)) & 1u);
             if (c <= thr[i]) valid |= 1ull << i;
         }
-        if (n >= win_lo && n >= 1 && ((full_mask >> (n - win_lo)) & 1u)) valid &= ~(1ull << m);   // same cell as the full candidate at column n
+        if (n >= 1 && ((full_mask >> (n - win_lo)) & 1u)) valid &= ~(1ull << m);   // same cell as the full candidate at column n
     }
     int best_m = 0, best_c = m + n, best_o = K1_NOMATCH, best_v = 0x7fffffff;
     // per-lane state machine: state 0 = fetch next candidate, 1 = walking back, 2 = finished
@@ -134,7 +148,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
     int ci = 0, cj = 0, cc = 0, c0 = 0, mt = 0, visit = 0;
     while (__any_sync(0xffffffffu, state != 2)) {
         if (state == 0) {
-            int i, j;
+            int i = 0, j = 0;
             bool have = true;
             if (full_mask) {
                 const int t = __ffs(full_mask) - 1;
@@ -146,19 +160,18 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
                 j = n; visit = n + 1 + (m - i);
                 if (i < best_m) { have = false; state = 2; }          // matches <= i: nothing left can win
             } else {
-                have = false; state = 2; i = 0; j = 0;
+                have = false; state = 2;
             }
             if (have) {
                 const int c = k1_cell_cost(ring, i, j);
                 if (j == n && i == best_m && c >= best_c) {
                     // could at best tie, and is visited later: skip
-                } else if (c == 0) {
-                    if (i > best_m || (i == best_m && (0 < best_c || visit < best_v))) { best_m = i; best_c = 0; best_o = j - i; best_v = visit; }
                 } else {
                     ci = i; cj = j; cc = c; c0 = c; mt = 0; state = 1;
                 }
             }
-        } else if (state == 1) {
+        }
+        if (state == 1) {
             // one step of cutadapt's predecessor choice, back towards a zero-cost (exact) cell
             int o = -1;
             bool done = false;
@@ -166,17 +179,17 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
             else if (cc == 0) { mt += ci; o = cj - ci; done = true; }
             else if (cj == 0) { o = 0; done = true; }
             else {
-                const int rb = pseq_isn<W>(p, cj - 1) ? 4 : pseq_base<W>(p, cj - 1);
-                const int ab = (int)((aw >> ((ci - 1) * 2)) & 3ull);
-                if (rb == ab) { mt++; ci--; cj--; }
+                const u32 eqm = peq8[pseq_base<W>(p, cj - 1) | (pseq_isn<W>(p, cj - 1) << 2)];
+                const u32 bit = 1u << (ci - 1);
+                if (eqm & bit) { mt++; ci--; cj--; }
                 else if (cj < win_lo || (cj - 1 != 0 && cj - 1 < win_lo)) { slow = true; state = 2; }   // needs a column outside the window
                 else {
-                    const int cd = k1_cell_cost(ring, ci - 1, cj - 1) + 1;
-                    const int cdel = k1_cell_cost(ring, ci, cj - 1) + 1;
-                    const int cins = k1_cell_cost(ring, ci - 1, cj) + 1;
-                    if (cd <= cdel && cd <= cins) { ci--; cj--; cc = cd - 1; }
-                    else if (cins <= cdel) { ci--; cc = cins - 1; }
-                    else { cj--; cc = cdel - 1; }
+                    const u32 mhs = ringh[(cj & (K1_RING - 1)) * K1_THREADS];
+                    const u32 mvp = (cj - 1 == 0) ? 0u : (u32)(ring[((cj - 1) & (K1_RING - 1)) * K1_THREADS] >> 32);
+                    cc--;
+                    if (mhs & bit) ci--;                  // insertion: from (i-1, j)
+                    else if (mvp & bit) cj--;             // deletion: from (i, j-1)
+                    else { ci--; cj--; }                  // mismatch: diagonal
                 }
             }
             if (done) {
@@ -196,14 +209,14 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
 // AdapterCutter(times=1) over all adapters: most matches wins, first wins ties.
 // Returns the new length, or K1_SLOW.  Warp-convergent.
 template <int W>
-__device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, u64 *ring)
+__device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, u64 *ring, u32 *ringh, const u32 *peq8)
 {
     int best_rstart = -1, best_matches = -1;
     bool slow = false;
     for (int a = 0; a < tp.n_adapters; a++) {
         if (tp.alen[a] > 32) { slow = true; continue; }
         int mt = 0;
-        const int rs = k1_match_fast<W>(p, n, tp, thr, a, ring, mt);
+        const int rs = k1_match_fast<W>(p, n, tp, thr, a, ring, ringh, peq8 + 8 * a, mt);
         if (rs == K1_SLOW) slow = true;
         else if (rs >= 0 && (best_rstart < 0 || mt > best_matches)) { best_rstart = rs; best_matches = mt; }
     }
@@ -241,19 +254,24 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
                  u64 n_records, int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, int force_slow)
 {
     __shared__ u64 ring[K1_RING * K1_THREADS];
+    __shared__ u32 ringh[K1_RING * K1_THREADS];
     __shared__ u32 slowq[K1_QCAP];
     __shared__ u32 slowq_n;
     __shared__ u32 sh_hist[32 * W + 1];
     __shared__ TrimParams tp;                       // dynamic indexing by adapter: keep it out of local memory
     __shared__ signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
+    __shared__ u32 peq8[MIRGE_MAX_ADAPTERS * 8];
     for (int b = threadIdx.x; b <= 32 * W; b += K1_THREADS) sh_hist[b] = 0;
     for (int b = threadIdx.x; b <= MIRGE_MAX_ADAPTER_LEN; b += K1_THREADS) thr[b] = thr_param.v[b];
     for (int b = threadIdx.x; b < (int)(sizeof(TrimParams) / 4); b += K1_THREADS)
         reinterpret_cast<u32 *>(&tp)[b] = reinterpret_cast<const u32 *>(&tp_param)[b];
+    if (threadIdx.x < MIRGE_MAX_ADAPTERS * 8)
+        peq8[threadIdx.x] = (threadIdx.x & 4) ? 0u : (u32)tp_param.peq[threadIdx.x >> 3][threadIdx.x & 3];
     if (threadIdx.x == 0) slowq_n = 0;
     __syncthreads();
     u32 my_kept = 0, my_slow = 0;
     u64 *my_ring = ring + threadIdx.x;
+    u32 *my_ringh = ringh + threadIdx.x;
     for (u64 r0 = (u64)blockIdx.x * K1_THREADS; r0 < n_records; r0 += (u64)gridDim.x * K1_THREADS) {
         const u64 r = r0 + threadIdx.x;
         const bool live = r < n_records;
@@ -272,7 +290,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
             if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); nf = n - cut; }
             else if (L < 0) { const int cut = (-L) < n ? (-L) : n; nf = n - cut; }
         } else if (tp.mode == 1) {
-            nf = force_slow ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring);   // warp-uniform branch
+            nf = force_slow ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring, my_ringh, peq8);   // warp-uniform branch
         }
         __syncwarp();
         if (live && nf == K1_SLOW) slowq[atomicAdd(&slowq_n, 1u)] = (u32)r;
