@@ -144,6 +144,14 @@ class Engine:
         self._ck(lib.mirge_export_tables(self.h, _ptr(q), _ptr(i), _ptr(t), _ptr(lh), _ptr(rp), _ptr(ra)))
         return dict(mir_quant=q, mir_iscan=i, lib_totals=t, len_hist=lh, round_processed=rp, round_aligned=ra)
 
+    def export_tables_prelim(self):
+        """Tables that exist before tally(): read-length histogram and per-round statistics."""
+        lh = np.zeros((self.max_read_len + 1, self.S), np.uint64)
+        rp = np.zeros(10, np.uint64)
+        ra = np.zeros(10, np.uint64)
+        self._ck(lib.mirge_export_tables(self.h, None, None, None, _ptr(lh), _ptr(rp), _ptr(ra)))
+        return dict(len_hist=lh, round_processed=rp, round_aligned=ra)
+
     # -- multi-GPU exchange -------------------------------------------------------
     def record_bytes(self):
         return int(lib.mirge_record_bytes(self.h))

@@ -170,6 +170,8 @@ def write_trim_collapse_fa(outdir, uniq, sample_names):
     """-tcf: <sample>.trim.collapse.fa, records >seq<rank>_<count> sorted by (count, seq) descending (quantReads.py:26-44)."""
     seqs = np.char.decode(uniq['seq'], 'ascii')
     for i, s in enumerate(sample_names):
+        if s is None:
+            continue
         c = uniq['counts'][:, i]
         sel = np.flatnonzero(c > 0)
         deco = sorted(zip(c[sel].tolist(), seqs[sel].tolist()), reverse=True)
