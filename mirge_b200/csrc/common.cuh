@@ -118,13 +118,18 @@ __host__ __device__ __forceinline__ u64 mix64(u64 x)
     x ^= x >> 33;
     return x;
 }
-// Hash over a canonical 4+2 word form so that W=2 and W=4 contexts (and the
-// host) agree on the owner of a sequence.
+// Hash of a key: only the words its length occupies take part, so W=2 and W=4
+// contexts (and the host) agree on the hash -- and the owner -- of a sequence.
 __host__ __device__ __forceinline__ u64 key_hash_words(const u64 *s, int W, const u64 *nm, int len)
 {
-    u64 h = 0x9E3779B97F4A7C15ULL ^ (u64)len;
-    for (int w = 0; w < 4; w++) h = mix64(h ^ (w < W ? s[w] : 0ull)) + 0x632BE59BD9B4E019ULL * (u64)(w + 1);
-    for (int w = 0; w < 2; w++) h = mix64(h ^ (w < W / 2 ? nm[w] : 0ull)) + 0xD6E8FEB86659FD93ULL * (u64)(w + 1);
+    u64 h = 0x9E3779B97F4A7C15ULL ^ ((u64)len * 0xD6E8FEB86659FD93ULL);
+    const int nb = (len + 31) >> 5, nn = (len + 63) >> 6;
+#pragma unroll
+    for (int w = 0; w < 4; w++)
+        if (w < W && w < nb) { h = (h ^ s[w]) * 0xFF51AFD7ED558CCDULL; h ^= h >> 32; }
+#pragma unroll
+    for (int w = 0; w < 2; w++)
+        if (w < W / 2 && w < nn) { h = (h ^ nm[w]) * 0xC4CEB9FE1A85EC53ULL; h ^= h >> 29; }
     return mix64(h);
 }
 // Owner rank of a key in the multi-GPU exchange = owner_hash(h) % n_ranks; re-mixed so
@@ -134,6 +139,46 @@ template <int W>
 __device__ __forceinline__ u64 pseq_hash(const PSeq<W> &p, int len)
 {
     return key_hash_words(p.s, W, p.nm, len);
+}
+
+// bit i of x -> bit 2i of the result
+__host__ __device__ __forceinline__ u64 spread32(u32 x)
+{
+    u64 v = x;
+    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+// 64-bit window (32 bases) of a W-word 2-bit array starting at base offset `so`
+template <int W>
+__device__ __forceinline__ u64 words_window64(const u64 *a, int so)
+{
+    const int ws = so >> 5, bs = (so & 31) * 2;
+    u64 lo = 0ull, hi = 0ull;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        if (w == ws) lo = a[w];
+        if (w == ws + 1) hi = a[w];
+    }
+    return bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+}
+
+// 32-bit window of a 1-bit-per-base mask (NW words) starting at base offset `so`
+template <int NW>
+__device__ __forceinline__ u32 mask_window32(const u64 *a, int so)
+{
+    const int ws = so >> 6, bs = so & 63;
+    u64 lo = 0ull, hi = 0ull;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        if (w == ws) lo = a[w];
+        if (w == ws + 1) hi = a[w];
+    }
+    return (u32)(bs ? ((lo >> bs) | (hi << (64 - bs))) : lo);
 }
 
 // ---------------------------------------------------------------------------

@@ -86,6 +86,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
 {
     // peq8[c | isN << 2]: match mask of read base c against the adapter (0 for N)
     const int m = tp.alen[a];
+    const u64 aw = tp.aw[a][0];
     u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
     int score = m;
     const int thr_m = thr[m];
@@ -105,6 +106,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
             }
         }
         const int jend = (nmax - j0) < 16 ? (nmax - j0) : 16;
+#pragma unroll 4
         for (int t = 0; t < jend; t++) {
             const int j = j0 + t + 1;
             const u32 Eq = peq8[(bw & 3u) | (((nb >> t) & 1u) << 2)];
@@ -168,6 +170,14 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
                     // could at best tie, and is visited later: skip
                 } else {
                     ci = i; cj = j; cc = c; c0 = c; mt = 0; state = 1;
+                    // common shape: c unmatched adapter bases at the read's end, i.e. c insertions
+                    // straight down column j to an exact cell -- settle it without stepping
+                    if (c > 0 && c < i) {
+                        const u32 chain = ((1u << c) - 1u) << (i - c);           // rows i-c+1 .. i
+                        const u32 mhs = ringh[(j & (K1_RING - 1)) * K1_THREADS];
+                        const u32 eqj = peq8[pseq_base<W>(p, j - 1) | (pseq_isn<W>(p, j - 1) << 2)];
+                        if ((mhs & chain) == chain && (eqj & chain) == 0u) { ci = i - c; cc = 0; }
+                    }
                 }
             }
         }
@@ -179,9 +189,19 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
             else if (cc == 0) { mt += ci; o = cj - ci; done = true; }
             else if (cj == 0) { o = 0; done = true; }
             else {
-                const u32 eqm = peq8[pseq_base<W>(p, cj - 1) | (pseq_isn<W>(p, cj - 1) << 2)];
+                // matches run diagonally: take the whole run of equal bases in one step
+                const int d = cj - ci;
                 const u32 bit = 1u << (ci - 1);
-                if (eqm & bit) { mt++; ci--; cj--; }
+                int run = 0;
+                if (d >= 0) {
+                    const u64 x = words_window64<W>(p.s, d) ^ aw;
+                    u64 mm = ((x | (x >> 1)) & 0x5555555555555555ull) | spread32(mask_window32<W / 2>(p.nm, d));
+                    if (ci < 32) mm &= (1ull << (2 * ci)) - 1ull;
+                    run = mm ? ci - 1 - ((63 - __clzll(mm)) >> 1) : ci;
+                } else if (peq8[pseq_base<W>(p, cj - 1) | (pseq_isn<W>(p, cj - 1) << 2)] & bit) {
+                    run = 1;
+                }
+                if (run > 0) { mt += run; ci -= run; cj -= run; }
                 else if (cj < win_lo || (cj - 1 != 0 && cj - 1 < win_lo)) { slow = true; state = 2; }   // needs a column outside the window
                 else {
                     const u32 mhs = ringh[(cj & (K1_RING - 1)) * K1_THREADS];

@@ -83,17 +83,6 @@ __global__ void k2_kmer_pass(LibView L, int k, int pass, u32 *__restrict__ bucke
 // ---------------------------------------------------------------------------
 // per-read search
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ u64 spread32(u32 x)
-{
-    u64 v = x;
-    v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
-    v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
-    v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
-    v = (v | (v << 2)) & 0x3333333333333333ull;
-    v = (v | (v << 1)) & 0x5555555555555555ull;
-    return v;
-}
-
 __device__ __forceinline__ int ref_of_gpos(const LibView &L, u32 g)
 {
     int lo = 0, hi = L.n_refs;
@@ -164,20 +153,6 @@ __device__ __forceinline__ void consider(const LibView &L, const Query<W> &q, u3
     const int r = ref_of_gpos(L, g);
     if ((u64)g + (u64)q.n > (u64)__ldg(L.ref_off + r + 1)) return;   // crosses the entry end
     best = key;
-}
-
-// 64-bit window (32 bases) of a W-word array starting at base offset `so`
-template <int W>
-__device__ __forceinline__ u64 words_window64(const u64 *a, int so)
-{
-    const int ws = so >> 5, bs = (so & 31) * 2;
-    u64 lo = 0ull, hi = 0ull;
-#pragma unroll
-    for (int w = 0; w < W; w++) {
-        if (w == ws) lo = a[w];
-        if (w == ws + 1) hi = a[w];
-    }
-    return bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
 }
 
 struct K2Arrays {
