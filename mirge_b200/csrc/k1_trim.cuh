@@ -7,6 +7,7 @@
 // window); output is the device hash table of unique sequences with per-sample
 // counts, the read-length histogram and the kept counter.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------
@@ -86,7 +87,11 @@ __device__ u32 table_upsert(const TableView<W> &T, const PSeq<W> &key, int len, 
         if (t == 0) {
             u32 old = atomicCAS(tagp, 0u, want);
             if (old == 0) {
-                u64 id = atomicAdd(T.n_unique, 1ull);
+                // dense ids come from ONE global counter: lanes inserting at the same time take a block of ids together
+                cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+                u64 id = 0;
+                if (g.thread_rank() == 0) id = atomicAdd(T.n_unique, (u64)g.size());
+                id = g.shfl(id, 0) + g.thread_rank();
                 u32 id32 = 0xFFFFFFFFu;
                 if (id < T.max_unique) {
                     id32 = (u32)id;
