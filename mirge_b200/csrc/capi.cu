@@ -35,7 +35,7 @@ static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
 
 struct DevLib {
     u64 *seq = nullptr, *amb = nullptr;
-    u32 *ref_off = nullptr;
+    u32 *ref_off = nullptr, *blk_ref = nullptr;
     int n_refs = 0;
     u32 total = 0;
     int ntabs = 0;
@@ -207,7 +207,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
 
 static void free_lib(DevLib &l)
 {
-    cudaFree(l.seq); cudaFree(l.amb); cudaFree(l.ref_off);
+    cudaFree(l.seq); cudaFree(l.amb); cudaFree(l.ref_off); cudaFree(l.blk_ref);
     for (int t = 0; t < l.ntabs; t++) { cudaFree(l.tab_off[t]); cudaFree(l.tab_pos[t]); }
     l = DevLib();
 }
@@ -477,6 +477,17 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
     for (int i = 0; i <= n_refs; i++) off32[i] = (u32)(n_refs ? offsets[i] : 0);
     CK(cudaMalloc(&l.ref_off, (size_t)(n_refs + 1) * sizeof(u32)));
     CK(cudaMemcpyAsync(l.ref_off, off32.data(), (size_t)(n_refs + 1) * sizeof(u32), cudaMemcpyHostToDevice, st));
+    {   // entry index at the start of every 64-base block (empty entries are skipped by the forward scan)
+        std::vector<u32> blk(total / 64 + 2);
+        int r = 0;
+        for (size_t b = 0; b < blk.size(); b++) {
+            const u64 g = (u64)b * 64;
+            while (r + 1 < n_refs && offsets[r + 1] <= g) r++;
+            blk[b] = (u32)r;
+        }
+        CK(cudaMalloc(&l.blk_ref, blk.size() * sizeof(u32)));
+        CK(cudaMemcpy(l.blk_ref, blk.data(), blk.size() * sizeof(u32), cudaMemcpyHostToDevice));
+    }
     if (total == 0) { CK(cudaStreamSynchronize(st)); return MIRGE_OK; }
     unsigned char *d_ascii = nullptr;
     CK(cudaMalloc(&d_ascii, total));
@@ -488,7 +499,7 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
     if (lib_id == MIRGE_LIB_MIRNA) ks = {4, 5, 6, 7, 8};
     else if (total >= (1u << 20)) ks = {8, 12};
     else ks = {8};
-    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.n_refs = n_refs; L.total = (u32)total;
+    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = n_refs; L.total = (u32)total;
     for (int k : ks) {
         if ((u64)k > total) continue;
         const u64 nb = 1ull << (2 * k);
@@ -544,7 +555,7 @@ static int annotate_impl(mirge_ctx *ctx)
     for (int r = 0; r < nrounds; r++) {
         const RoundSpec &rs = ROUNDS[r];
         const DevLib &l = ctx->libs[rs.lib];
-        LibView L; L.seq = l.total ? l.seq : nullptr; L.amb = l.amb; L.ref_off = l.ref_off; L.n_refs = l.n_refs; L.total = l.total;
+        LibView L; L.seq = l.total ? l.seq : nullptr; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = l.n_refs; L.total = l.total;
         RoundParams R;
         memset(&R, 0, sizeof R);
         R.round = r; R.len_filter = rs.len_filter; R.mode = rs.mode; R.param = rs.param; R.trim5 = rs.trim5; R.trim3 = rs.trim3;

@@ -104,18 +104,34 @@ k0_pack(const unsigned char *__restrict__ text, const u32 *__restrict__ line_sta
         for (int w = 0; w < W; w++) s[w] = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) nm[w] = 0;
-        if (!bad) {
+        if (!bad && sl > 0) {
+            // four bases per step: aligned 32-bit loads, realigned with a funnel shift;
+            // 2-bit codes and the non-ACGT flags are computed on all four bytes at once
+            const u32 *t32 = reinterpret_cast<const u32 *>(text) + (a1 >> 2);
+            const u32 sh8 = (a1 & 3u) * 8u;
+            u32 wprev = __ldg(t32);
+            const int ngroups = (sl + 3) >> 2;
 #pragma unroll
             for (int w = 0; w < W; w++) {
-                u64 acc = 0, nacc = 0;
-                int lo = w * 32;
-                for (int i = 0; i < 32 && lo + i < sl; i++) {
-                    int c = base_code(text[a1 + lo + i]);
-                    if (c > 3) { nacc |= 1ull << i; c = 0; }
-                    acc |= (u64)c << (2 * i);
+                u64 acc = 0;
+                u32 nacc = 0;
+                for (int gi = w * 8; gi < w * 8 + 8 && gi < ngroups; gi++) {
+                    const u32 wnext = __ldg(t32 + gi + 1);
+                    const u32 v = __funnelshift_r(wprev, wnext, sh8);       // bytes a1+4gi .. a1+4gi+3
+                    wprev = wnext;
+                    const u32 up = v & 0xDFDFDFDFu;
+                    const u32 ok = __vcmpeq4(up, 0x41414141u) | __vcmpeq4(up, 0x43434343u) | __vcmpeq4(up, 0x47474747u) |
+                                   __vcmpeq4(up, 0x54545454u) | __vcmpeq4(up, 0x55555555u);        // A C G T U
+                    u32 code = (((v >> 1) ^ (v >> 2)) & 0x03030303u) & ok;   // A=0 C=1 G=2 T/U=3, others 0
+                    u32 packed = (code * 0x01041040u) >> 24;                  // 4 x 2 bits
+                    u32 nbits = (((~ok) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
+                    const int left = sl - gi * 4;
+                    if (left < 4) { packed &= (1u << (2 * left)) - 1u; nbits &= (1u << left) - 1u; }
+                    acc |= (u64)packed << ((gi & 7) * 8);
+                    nacc |= nbits << ((gi & 7) * 4);
                 }
                 s[w] = acc;
-                nm[w >> 1] |= nacc << ((w & 1) * 32);
+                nm[w >> 1] |= (u64)nacc << ((w & 1) * 32);
             }
         }
         // quality_trim_index(qualities, cutoff_front=0, cutoff_back, base)

@@ -20,6 +20,7 @@ struct LibView {
     const u64 *seq;        // 2-bit packed concatenation (zero padded by >= 5 words)
     const u64 *amb;        // 1 bit per base, set for non-ACGT (zero padded)
     const u32 *ref_off;    // [n_refs + 1] base offsets
+    const u32 *blk_ref;    // [total / 64 + 1] entry holding the first base of each 64-base block
     int n_refs;
     u32 total;
 };
@@ -83,14 +84,12 @@ __global__ void k2_kmer_pass(LibView L, int k, int pass, u32 *__restrict__ bucke
 // ---------------------------------------------------------------------------
 // per-read search
 // ---------------------------------------------------------------------------
+// entry that holds global base offset g: block table + short forward scan
 __device__ __forceinline__ int ref_of_gpos(const LibView &L, u32 g)
 {
-    int lo = 0, hi = L.n_refs;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(L.ref_off + mid) <= g) lo = mid; else hi = mid;
-    }
-    return lo;
+    int r = (int)__ldg(L.blk_ref + (g >> 6));
+    while (__ldg(L.ref_off + r + 1) <= g) r++;
+    return r;
 }
 
 template <int W>

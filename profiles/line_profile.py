@@ -39,6 +39,10 @@ def main():
             off2line[int(m.group(1), 16)] = cur
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    # a report may hold several launches: keep the N-th one (env LAUNCH, default 0)
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+    which = int(os.environ.get('LAUNCH', '0'))
+    rows = rows[starts[which]:starts[which + 1]]
     hdr, data = rows[1], rows[2:]
     iA, iE, iS, iT = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples'), hdr.index('Thread Instructions Executed')
     base = int(data[0][iA], 16)
