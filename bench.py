@@ -18,7 +18,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -35,7 +34,7 @@ READ_LEN = 50
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--reads', type=int, default=25_000_000, help='raw reads per GPU per step (BASELINE configs[1]: 25M)')
@@ -50,25 +49,36 @@ def workload_name(args):
             'synthetic libs scale %.2f' % (args.reads // 1_000_000, READ_LEN, args.scale))
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md):
+    one streaming `nvidia-smi -lms 50` process, started before and killed after."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu):
-        super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            time.sleep(0.05)
+    def start(self):
+        pass
+
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        for line in out.strip().split('\n'):
+            if line.strip():
+                self.rows.append([x.strip() for x in line.split(',')])
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
@@ -80,6 +90,19 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': sorted(reasons), 'samples': len(self.rows)}
+
+
+def ncu_traffic(kernel, n_reads):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture of this workload, else None."""
+    path = os.path.join(ROOT, 'profiles', 'r1_k1_full_metrics.txt')
+    if kernel != 'k1_trim_collapse' or n_reads != 25_000_000 or not os.path.exists(path):
+        return None
+    tot = 0.0
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            tot += float(f[1]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[f[2]]
+    return tot or None
 
 
 def build_world(args):
@@ -226,7 +249,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_res, launches, prof = timed(True, args.steps, args.warmup, profile=True)
-    sampler.stop_flag = True
+    sampler.stop()
     # size-independent correctness properties at full size (tests/ hold the bit-exact oracle comparisons)
     p, k, U = eng.stats()
     slow_frac = eng.slow_reads() / float(n_reads)
@@ -260,7 +283,8 @@ def run_ours(args):
         per_launch_ms = dom_ms / dom_n
         ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if ab else None
         roof = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                'frac': (ach / peak) if ach else None, 'traffic': None,
+                'frac': (ach / peak) if ach else None, 'traffic': ncu_traffic(dom, n_reads),
+                'algorithmic_bytes_per_launch': per_launch_bytes,
                 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)',
                 'kernel_ms_per_step': {n: round(v[0] / args.steps, 4) for n, v in prof.items() if v[1] > 0},
                 'share_of_step': dom_ms / ms_res}
