@@ -260,8 +260,14 @@ k1_export_records(TableView<W> T, u64 n_unique, int n_parts, int rec_bytes, int 
         const int len = T.ulen[id];
         const u64 h = key_hash_words(s, W, nm, len);
         const int part = (int)(owner_hash(h) % (u64)n_parts);
-        if (count_only) { atomicAdd(&part_counts[part], 1ull); continue; }
-        const u64 dst = atomicAdd(&part_cursor[part], 1ull);
+        // few destinations, many records: lanes bound for the same rank share one atomic
+        const unsigned peers = __match_any_sync(__activemask(), part);
+        const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+        const u32 rank = __popc(peers & ((1u << lane) - 1u));
+        if (count_only) { if (lane == leader) atomicAdd(&part_counts[part], (u64)__popc(peers)); continue; }
+        u64 dst = 0;
+        if (lane == leader) dst = atomicAdd(&part_cursor[part], (u64)__popc(peers));
+        dst = __shfl_sync(peers, dst, leader) + rank;
         u64 *q = reinterpret_cast<u64 *>(out + dst * (u64)rec_bytes);
 #pragma unroll
         for (int w = 0; w < W; w++) q[w] = s[w];
