@@ -428,3 +428,76 @@ def run_tables(o, sampleList, mirna_names, merge_lines, canoRatio='0.1'):
                 report=annotation_report_csv(sampleList, logDic, o.spike_in),
                 counts=mir_counts_csv(sampleList, logDic, mirDic),
                 rpm=mir_rpm_csv(sampleList, logDic, mirDic))
+
+
+def isomir_tables(seqDic, sampleList, logDic):
+    """writeDataToCSV.py:584-607 (isomirDic) and :1090-1170 (isomirs.csv, isomirs.samples.csv), literal.
+    Returns (isomirs.csv text, isomirs.samples.csv text); row order is Python-2 dict order upstream."""
+    import math
+
+    def calcEntropy(inputList):                      # writeDataToCSV.py:344-351
+        sum1 = sum(inputList)
+        entropy = 0
+        for i in range(len(inputList)):
+            if inputList[i] > 1:
+                freq = float(inputList[i]) / sum1
+                entropy = entropy + -1 * freq * math.log(freq, 2)
+        return entropy
+
+    isomirDic = {}
+    for seqKey in seqDic.keys():
+        if seqDic[seqKey]['annot'][0] > 0:
+            isomir = seqDic[seqKey]['annot'][9]
+            mirna = seqDic[seqKey]['annot'][1]
+            if isomir != '' or mirna != '':
+                if isomir != '':
+                    key, key2 = isomir, 'isomirs'
+                else:
+                    key, key2 = mirna, 'mirnas'
+                if '.SNP' in key:
+                    key = key.split('.SNP')[0]
+                if key not in isomirDic:
+                    isomirDic[key] = {'mirnas': {}, 'isomirs': {}}
+                isomirDic[key][key2][seqKey] = [seqDic[seqKey]['quant'][i] for i in range(len(sampleList))]
+    out1 = ['miRNA,sequence' + ''.join(',' + s for s in sampleList) + ',Entropy\n']
+    out2 = ['miRNA' + ''.join(',' + s + ' isomir+miRNA Entropy' + ',' + s + ' Canonical Sequence' + ',' + s + ' Canonical RPM'
+                              + ',' + s + ' Top Isomir RPM' for s in sampleList) + '\n']
+    for miRNA in isomirDic.keys():
+        sampleIsomirs = {i: [] for i in range(len(sampleList))}
+        samplemiRNAs = [0] * len(sampleList)
+        for miRNASeq in isomirDic[miRNA]['mirnas'].keys():
+            sampleArray = isomirDic[miRNA]['mirnas'][miRNASeq]
+            for i in range(len(sampleArray)):
+                samplemiRNAs[i] = samplemiRNAs[i] + sampleArray[i]
+        for miRNASeq in isomirDic[miRNA]['isomirs'].keys():
+            entry = [miRNA, miRNASeq]
+            sampleArray = isomirDic[miRNA]['isomirs'][miRNASeq]
+            for i in range(len(sampleArray)):
+                sampleIsomirs[i].append(sampleArray[i])
+            entropy = calcEntropy(sampleArray)
+            maxEntropy = math.log(len(sampleArray), 2)
+            entropy = 'NA' if maxEntropy == 0 else py2_str_float(entropy / maxEntropy)
+            for i in range(len(sampleArray)):
+                sampleArray[i] = py2_str_float(sampleArray[i] * 1000000.0 / logDic['quantStats'][i]['mirnaReadsFiltered'])
+            out1.append(','.join(entry + sampleArray + [str(entropy)]) + '\n')
+        isomirOut = [miRNA]
+        for sampleLane in range(len(sampleList)):
+            rpmFactor = 1000000.0 / logDic['quantStats'][sampleLane]['mirnaReadsFiltered']
+            if len(sampleIsomirs[sampleLane]) > 0:
+                topIsomir = max(sampleIsomirs[sampleLane]) * rpmFactor
+                isomirSum = sum(sampleIsomirs[sampleLane]) * rpmFactor
+                sampleIsomirs[sampleLane].append(samplemiRNAs[sampleLane])
+                sampleEntropyWithmiRNA = calcEntropy(sampleIsomirs[sampleLane])
+                miRNARPM = samplemiRNAs[sampleLane] * rpmFactor
+                maxEntropy = len(sampleIsomirs[sampleLane])
+                if maxEntropy > 1:
+                    sampleEntropyWithmiRNA = py2_str_float(sampleEntropyWithmiRNA / (math.log(maxEntropy, 2)))
+                else:
+                    sampleEntropyWithmiRNA = 'NA'
+                isomirOut.append(sampleEntropyWithmiRNA)
+                combined = miRNARPM + isomirSum
+                isomirOut.append(py2_str_float(100.0 * miRNARPM / combined) if combined > 0 else 'NA')
+                isomirOut.append(py2_str_float(miRNARPM))
+                isomirOut.append(py2_str_float(topIsomir))
+                out2.append(','.join(isomirOut) + '\n')
+    return ''.join(out1), ''.join(out2)

@@ -58,7 +58,11 @@ def test_cli_matches_oracle_tables(tmp_path, small_world, world_dir, oracle_mod,
     fa = open(os.path.join(out, 'sampleA.trim.collapse.fa')).read().split('\n')
     top = max(tabs['seqDic'].items(), key=lambda kv: (kv[1]['quant'][0], kv[0]))
     assert fa[0] == '>seq1_%d' % top[1]['quant'][0] and fa[1] == top[0]
-    assert os.path.getsize(os.path.join(out, 'isomirs.csv')) > 100
+    want1, want2 = oracle_mod.isomir_tables(tabs['seqDic'], names, tabs['logDic'])       # -di tables, row order unspecified upstream
+    for fn, want in (('isomirs.csv', want1), ('isomirs.samples.csv', want2)):
+        got_lines = open(os.path.join(out, fn)).read().strip().split('\n')
+        want_lines = want.strip().split('\n')
+        assert got_lines[0] == want_lines[0] and sorted(got_lines[1:]) == sorted(want_lines[1:]) and len(got_lines) > 10
 
 
 def test_cli_aborts_when_a_sample_has_no_mirna(tmp_path, world_dir):
