@@ -546,6 +546,9 @@ static int annotate_impl(mirge_ctx *ctx)
 {
     cudaStream_t st = ctx->stream;
     CK(cudaMemsetAsync(ctx->d_round_of, 0, ctx->max_unique, st));
+    CK(cudaMemsetAsync(ctx->d_mm_of, 0, ctx->max_unique, st));              // exports are deterministic for un-annotated sequences too
+    CK(cudaMemsetAsync(ctx->d_ref_of, 0, ctx->max_unique * sizeof(int), st));
+    CK(cudaMemsetAsync(ctx->d_pos_of, 0, ctx->max_unique * sizeof(int), st));
     CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 1) * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), st));
     K2Arrays A;
