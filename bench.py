@@ -18,6 +18,7 @@ import json
 import os
 import subprocess
 import sys
+import threading
 import time
 
 import numpy as np
@@ -49,36 +50,29 @@ def workload_name(args):
             'synthetic libs scale %.2f' % (args.reads // 1_000_000, READ_LEN, args.scale))
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md):
-    one streaming `nvidia-smi -lms 50` process, started before and killed after."""
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run (B200_PROFILING.md)."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu):
-        self.rows, self.proc = [], None
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
 
-    def start(self):
-        pass
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self):
-        if self.proc is None:
-            return
-        time.sleep(0.12)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ''
-        for line in out.strip().split('\n'):
-            if line.strip():
-                self.rows.append([x.strip() for x in line.split(',')])
+        self.stop_flag = True
+        self.join(timeout=6)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
@@ -251,7 +245,6 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_res, launches, prof = timed(True, args.steps, args.warmup, profile=True)
-    sampler.stop()
     # size-independent correctness properties at full size (tests/ hold the bit-exact oracle comparisons)
     p, k, U = eng.stats()
     slow_frac = eng.slow_reads() / float(n_reads)
@@ -262,7 +255,8 @@ def run_ours(args):
     assert int(p[sample]) == n_reads, 'processed != reads fed'
     if N == 1:
         assert int(tot[sample, 1:11].sum()) == int(k[sample]), 'library totals do not add up to kept reads'
-    ms_e2e, _, _ = timed(False, args.steps, max(1, args.warmup // 2))
+    ms_e2e, _, _ = timed(False, args.steps, max(3, args.warmup))
+    sampler.stop()
     d2h = sum(int(np.asarray(v).nbytes) for v in eng.export_tables().values())
     total_reads = n_reads * N
     value = total_reads * args.steps / (ms_res / 1e3)
