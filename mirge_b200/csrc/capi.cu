@@ -578,6 +578,10 @@ static int annotate_impl(mirge_ctx *ctx)
 int mirge_annotate(mirge_ctx *ctx)
 {
     CK(cudaSetDevice(ctx->device));
+    {   // a full table would leave the unique counter beyond the arrays the rounds index
+        int rc = mirge_sync(ctx);
+        if (rc) return rc;
+    }
     return ctx->W == 2 ? annotate_impl<2>(ctx) : annotate_impl<4>(ctx);
 }
 
