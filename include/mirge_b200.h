@@ -149,10 +149,11 @@ uint64_t mirge_hash_sequence(const char *seq, int len);
 int mirge_profile_enable(mirge_ctx *ctx, int on);
 /* ms[k], launches[k] accumulated since enable; names[k] static strings. */
 int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const char **names);
-/* Test hook: force_slow = 1 routes every read through the literal banded
- * cutadapt DP instead of the bit-vector fast path (-1 leaves it unchanged);
- * slow_reads (may be NULL) receives the number of reads that took the literal
- * DP so far.  Results are identical either way. */
+/* Test hook: force_slow = 1 sends every read through the slow queue (all-column
+ * bit-vector search), 3 through the literal banded cutadapt DP, 0 restores the
+ * windowed fast path, -1 leaves the setting unchanged; slow_reads (may be NULL)
+ * receives the number of reads that went through the slow queue so far.
+ * Results are identical in every mode. */
 int mirge_debug(mirge_ctx *ctx, int force_slow, uint64_t *slow_reads);
 /* Number of kernels this library has launched on the context so far. */
 uint64_t mirge_launch_count(const mirge_ctx *ctx);

@@ -244,13 +244,131 @@ __device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimP
     return best_rstart >= 0 ? best_rstart : n;
 }
 
+// Per-thread variant of k1_match_fast for the reads the windowed version could not
+// settle (walks that leave the 16-column ring, full-length inexact occurrences far
+// from the read end): the same bit-vector algorithm, but the vectors of EVERY column
+// are kept (thread-local arrays), so nothing is out of reach.  Not warp-collective;
+// run by converged threads when the slow queue is drained.
 template <int W>
-__device__ __forceinline__ int k1_trim_slow(const PSeq<W> &p, int n, const TrimParams &tp)
+__device__ int k1_match_full(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, int a,
+                             const u32 *peq8, int &matches_out)
+{
+    const int m = tp.alen[a];
+    const u64 aw = tp.aw[a][0];
+    u64 cv[32 * W];        // column j -> cv[j-1] = Pv | Mv << 32
+    u32 ch[32 * W];        // column j -> ch[j-1] = shifted negative horizontal deltas
+    u64 fullc[W / 2];      // bit j-1: inexact full-length candidate ending at column j
+#pragma unroll
+    for (int w = 0; w < W / 2; w++) fullc[w] = 0;
+    u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
+    int score = m;
+    const int thr_m = thr[m], top = m - 1;
+    for (int j = 1; j <= n; j++) {
+        const u32 Eq = peq8[pseq_base<W>(p, j - 1) | (pseq_isn<W>(p, j - 1) << 2)];
+        const u32 Xv = Eq | Mv;
+        const u32 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        u32 Ph = Mv | ~(Xh | Pv);
+        u32 Mh = Pv & Xh;
+        score += (int)((Ph >> top) & 1u) - (int)((Mh >> top) & 1u);
+        Ph <<= 1; Mh <<= 1;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+        cv[j - 1] = (u64)Pv | ((u64)Mv << 32);
+        ch[j - 1] = Mh;
+        if (score == 0) { matches_out = m; return j - m; }           // str.find: leftmost exact occurrence
+        if (score <= thr_m) {
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) if (((j - 1) >> 6) == w) fullc[w] |= 1ull << ((j - 1) & 63);
+        }
+    }
+    u64 valid = 0;
+    {
+        int c = 0;
+        for (int i = 1; i <= m; i++) {
+            c += (int)((Pv >> (i - 1)) & 1u) - (int)((Mv >> (i - 1)) & 1u);
+            if (c <= thr[i]) valid |= 1ull << i;
+        }
+    }
+    int best_m = 0, best_c = m + n, best_o = K1_NOMATCH, best_v = 0x7fffffff;
+    int fw = 0;            // full-candidate word being scanned
+    for (;;) {
+        int i, j, visit;
+        while (fw < W / 2) {
+            u64 f = 0;
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) if (fw == w) f = fullc[w];
+            if (f) break;
+            fw++;
+        }
+        if (fw < W / 2) {
+            u64 f = 0;
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) if (fw == w) f = fullc[w];
+            const int t = __ffsll((long long)f) - 1;
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) if (fw == w) fullc[w] &= fullc[w] - 1;
+            i = m; j = fw * 64 + t + 1; visit = j;
+        } else if (valid) {
+            i = 63 - __clzll(valid);
+            valid &= ~(1ull << i);
+            if (i < best_m) break;
+            j = n; visit = n + 1 + (m - i);
+        } else {
+            break;
+        }
+        const u64 vj = cv[j - 1];
+        const u32 low = (i >= 32) ? 0xFFFFFFFFu : ((1u << i) - 1u);
+        const int c = __popc((u32)vj & low) - __popc((u32)(vj >> 32) & low);
+        if (j == n && i == best_m && c >= best_c) continue;
+        int ci = i, cj = j, cc = c, mt = 0, o = -1;
+        for (;;) {
+            if (ci == 0) { o = cj; break; }
+            if (cc == 0) { mt += ci; o = cj - ci; break; }
+            if (cj == 0) { o = 0; break; }
+            const int d = cj - ci;
+            const u32 bit = 1u << (ci - 1);
+            int run = 0;
+            if (d >= 0) {
+                const u64 x = words_window64<W>(p.s, d) ^ aw;
+                u64 mm = ((x | (x >> 1)) & 0x5555555555555555ull) | spread32(mask_window32<W / 2>(p.nm, d));
+                if (ci < 32) mm &= (1ull << (2 * ci)) - 1ull;
+                run = mm ? ci - 1 - ((63 - __clzll(mm)) >> 1) : ci;
+            } else if (peq8[pseq_base<W>(p, cj - 1) | (pseq_isn<W>(p, cj - 1) << 2)] & bit) {
+                run = 1;
+            }
+            if (run > 0) { mt += run; ci -= run; cj -= run; continue; }
+            const u32 mhs = ch[cj - 1];
+            const u32 mvp = (cj - 1 == 0) ? 0u : (u32)(cv[cj - 2] >> 32);
+            cc--;
+            if (mhs & bit) ci--;
+            else if (mvp & bit) cj--;
+            else { ci--; cj--; }
+        }
+        if (mt > best_m || (mt == best_m && (c < best_c || (c == best_c && visit < best_v)))) {
+            best_m = mt; best_c = c; best_o = o; best_v = visit;
+        }
+    }
+    matches_out = best_m;
+    return best_o;
+}
+
+// Slow-queue reads: all-column bit-vector search per adapter (<= 32 nt), else the
+// literal banded DP (match_back -> locate_back).
+template <int W>
+__device__ __forceinline__ int k1_trim_slow(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, const u32 *peq8,
+                                            bool literal)
 {
     int best_rstart = -1, best_matches = -1;
     for (int a = 0; a < tp.n_adapters; a++) {
-        int rs, mt;
-        if (match_back<W>(p, n, tp, a, rs, mt) && (best_rstart < 0 || mt > best_matches)) { best_rstart = rs; best_matches = mt; }
+        int rs = -1, mt = 0;
+        bool found;
+        if (tp.alen[a] <= 32 && !literal) {
+            rs = k1_match_full<W>(p, n, tp, thr, a, peq8 + 8 * a, mt);
+            found = rs >= 0;
+        } else {
+            found = match_back<W>(p, n, tp, a, rs, mt);
+        }
+        if (found && (best_rstart < 0 || mt > best_matches)) { best_rstart = rs; best_matches = mt; }
     }
     return best_rstart >= 0 ? best_rstart : n;
 }
@@ -310,7 +428,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
             if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); nf = n - cut; }
             else if (L < 0) { const int cut = (-L) < n ? (-L) : n; nf = n - cut; }
         } else if (tp.mode == 1) {
-            nf = force_slow ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring, my_ringh, peq8);   // warp-uniform branch
+            nf = (force_slow & 3) ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring, my_ringh, peq8);   // warp-uniform branch
         }
         __syncwarp();
         if (live && nf == K1_SLOW) slowq[atomicAdd(&slowq_n, 1u)] = (u32)r;
@@ -325,7 +443,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
                 PSeq<W> ps;
                 int ns;
                 k1_load_record<W>(bases, nmask, meta, (u64)slowq[q], ps, ns);
-                const int nfs = k1_trim_slow<W>(ps, ns, tp);
+                const int nfs = k1_trim_slow<W>(ps, ns, tp, thr, peq8, (force_slow & 2) != 0);
                 my_kept += k1_finish<W>(ps, nfs, tp, T, sample, sh_hist) ? 1u : 0u;
                 my_slow++;
             }

@@ -167,9 +167,10 @@ class Engine:
     def launch_count(self):
         return int(lib.mirge_launch_count(self.h))
 
-    def force_slow_path(self, on=True):
-        """Test hook: run every read through the literal cutadapt DP."""
-        self._ck(lib.mirge_debug(self.h, int(on), None))
+    def force_slow_path(self, on=True, literal=False):
+        """Test hook: send every read through the slow queue -- the all-column bit-vector search, or
+        (literal=True) the cell-for-cell cutadapt DP."""
+        self._ck(lib.mirge_debug(self.h, (3 if literal else 1) if on else 0, None))
 
     def slow_reads(self):
         n = np.zeros(1, np.uint64)

@@ -54,7 +54,7 @@ def adversarial_reads(rng, adapter, n, maxlen=64, alphabet='ACGT'):
     return reads
 
 
-def _tables(O, reads_fq, adapter, max_read_len=64, force_slow=False, **kw):
+def _tables(O, reads_fq, adapter, max_read_len=64, force_slow=False, literal=False, **kw):
     from mirge_b200.engine import Engine
     o = O.Oracle(1, False, adapter)
     o.feed_fastq(0, reads_fq, 33)
@@ -63,7 +63,7 @@ def _tables(O, reads_fq, adapter, max_read_len=64, force_slow=False, **kw):
     e = Engine(1, False, 1 << 20, max_read_len)
     e.set_adapter(adapter, **kw)
     if force_slow:
-        e.force_slow_path(True)
+        e.force_slow_path(True, literal)
     e.feed_fastq(0, reads_fq, 33)
     ee = e.export_unique()
     got = {s.decode(): int(c[0]) for s, c in zip(ee['seq'], ee['counts'])}
@@ -82,8 +82,10 @@ def test_adversarial_reads_fast_and_slow(oracle_mod, adapter):
     want, got, slow, n = _tables(oracle_mod, fq, adapter)
     assert got == want
     assert slow < n          # the fast path is actually taken
-    want2, got2, slow2, n2 = _tables(oracle_mod, fq, adapter, force_slow=True)
+    want2, got2, slow2, n2 = _tables(oracle_mod, fq, adapter, force_slow=True)               # all-column bit-vector path
     assert got2 == want2 and slow2 == n2
+    want3, got3, slow3, n3 = _tables(oracle_mod, fq, adapter, force_slow=True, literal=True)  # literal cutadapt DP
+    assert got3 == want3 and slow3 == n3
 
 
 def test_long_adapter_and_long_reads(oracle_mod):
