@@ -23,7 +23,7 @@
 #include "k1_trim.cuh"
 
 #define K1_THREADS 128
-#define K1_RING 16
+#define K1_RING 8
 #define K1_QCAP (3 * K1_THREADS)
 
 struct K1Counters {
