@@ -497,8 +497,8 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
     // short as 13 nt (k = 4..8); the big mRNA library gets a 12-mer table.
     std::vector<int> ks;
     if (lib_id == MIRGE_LIB_MIRNA) ks = {4, 5, 6, 7, 8};
-    else if (total >= (1u << 20)) ks = {8, 12};
-    else ks = {8};
+    else if (total >= (1u << 20)) ks = {8, 10, 12};
+    else ks = {8, 10};          // longer seeds for reads that allow them: far fewer candidates to verify
     LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = n_refs; L.total = (u32)total;
     for (int k : ks) {
         if ((u64)k > total) continue;
