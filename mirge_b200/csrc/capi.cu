@@ -650,7 +650,7 @@ int mirge_tally(mirge_ctx *ctx)
                                                                                    ctx->d_counts, ctx->d_round_of, S, partial);
       k3_seg_reduce<<<grid_for((u64)n_seg * 32, 256, 148 * 8), 256, 0, st>>>(partial, chunk_off, n_seg, S, seg_q, seg_i, seg_u); }
     { ProfScope ps(ctx, KID_K3_FINAL);
-      k3_finalize<<<(S + 63) / 64, 64, 0, st>>>(seg_q, seg_i, seg_u, n_mir, S, ctx->d_mir_quant, ctx->d_mir_iscan, ctx->d_lib_totals); }
+      k3_finalize<<<S, 256, 0, st>>>(seg_q, seg_i, seg_u, n_mir, S, ctx->d_mir_quant, ctx->d_mir_iscan, ctx->d_lib_totals); }
     CK(cudaGetLastError());
     ctx->tallied = true;
     return MIRGE_OK;

@@ -24,7 +24,6 @@
 
 #define K1_THREADS 128
 #define K1_RING 8
-#define K1_QCAP (3 * K1_THREADS)
 
 struct K1Counters {
     u64 *kept;        // [S]
@@ -393,8 +392,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
 {
     __shared__ u64 ring[K1_RING * K1_THREADS];
     __shared__ u32 ringh[K1_RING * K1_THREADS];
-    __shared__ u32 slowq[K1_QCAP];
-    __shared__ u32 slowq_n;
+    __shared__ u32 slowq[K1_THREADS / 32][64];     // one queue per warp: no CTA-wide barrier in the main loop
     __shared__ u32 sh_hist[32 * W + 1];
     __shared__ TrimParams tp;                       // dynamic indexing by adapter: keep it out of local memory
     __shared__ signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
@@ -405,8 +403,9 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
         reinterpret_cast<u32 *>(&tp)[b] = reinterpret_cast<const u32 *>(&tp_param)[b];
     if (threadIdx.x < MIRGE_MAX_ADAPTERS * 8)
         peq8[threadIdx.x] = (threadIdx.x & 4) ? 0u : (u32)tp_param.peq[threadIdx.x >> 3][threadIdx.x & 3];
-    if (threadIdx.x == 0) slowq_n = 0;
     __syncthreads();
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 qn = 0;                                     // entries in this warp's queue (warp-uniform)
     u32 my_kept = 0, my_slow = 0;
     u64 *my_ring = ring + threadIdx.x;
     u32 *my_ringh = ringh + threadIdx.x;
@@ -431,25 +430,27 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
             nf = (force_slow & 3) ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring, my_ringh, peq8);   // warp-uniform branch
         }
         __syncwarp();
-        if (live && nf == K1_SLOW) slowq[atomicAdd(&slowq_n, 1u)] = (u32)r;
+        {   // queue the reads the windowed search could not settle
+            const unsigned sm = __ballot_sync(0xffffffffu, live && nf == K1_SLOW);
+            if (live && nf == K1_SLOW) slowq[wid][qn + __popc(sm & ((1u << lane) - 1u))] = (u32)r;
+            qn += __popc(sm);
+        }
         if (live && nf != K1_SLOW) my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
-        __syncthreads();
-        // drain the slow queue with converged threads once it could overflow on the next
-        // tile (every tile adds at most K1_THREADS entries), and after the last tile
-        const u32 qn = slowq_n;
+        __syncwarp();
+        // drain 32 at a time (a full warp of slow reads), and whatever is left after the last tile
         const bool last_tile = r0 + (u64)gridDim.x * K1_THREADS >= n_records;
-        if (qn && (qn > K1_QCAP - K1_THREADS || last_tile)) {
-            for (u32 q = threadIdx.x; q < qn; q += K1_THREADS) {
+        while (qn >= 32 || (last_tile && qn > 0)) {
+            const u32 take = qn < 32 ? qn : 32;
+            if (lane < take) {
                 PSeq<W> ps;
                 int ns;
-                k1_load_record<W>(bases, nmask, meta, (u64)slowq[q], ps, ns);
+                k1_load_record<W>(bases, nmask, meta, (u64)slowq[wid][qn - take + lane], ps, ns);
                 const int nfs = k1_trim_slow<W>(ps, ns, tp, thr, peq8, (force_slow & 2) != 0);
                 my_kept += k1_finish<W>(ps, nfs, tp, T, sample, sh_hist) ? 1u : 0u;
                 my_slow++;
             }
-            __syncthreads();
-            if (threadIdx.x == 0) slowq_n = 0;
-            __syncthreads();
+            qn -= take;
+            __syncwarp();
         }
     }
 #pragma unroll

@@ -210,23 +210,35 @@ k3_seg_reduce(const i64 *__restrict__ partial, const u32 *__restrict__ chunk_off
     }
 }
 
-// Fold the segment sums into the output tables: one thread per sample.
-__global__ void k3_finalize(const i64 *__restrict__ seg_q, const i64 *__restrict__ seg_i, const i64 *__restrict__ seg_u,
-                            int n_mir, int S, i64 *__restrict__ mir_quant, i64 *__restrict__ mir_iscan,
-                            i64 *__restrict__ lib_totals)
+// Fold the segment sums into the output tables: one 256-thread block per sample.
+__global__ void __launch_bounds__(256)
+k3_finalize(const i64 *__restrict__ seg_q, const i64 *__restrict__ seg_i, const i64 *__restrict__ seg_u,
+            int n_mir, int S, i64 *__restrict__ mir_quant, i64 *__restrict__ mir_iscan,
+            i64 *__restrict__ lib_totals)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
+    __shared__ i64 red[2][8];
+    const int s = blockIdx.x;
     i64 uniq = 0, mirna = 0;
-    for (int m = 0; m < n_mir; m++) {
+    for (int m = threadIdx.x; m < n_mir; m += blockDim.x) {
         const i64 q = seg_q[(u64)m * S + s];
         mir_quant[(u64)m * S + s] = q;
         mir_iscan[(u64)m * S + s] = seg_i[(u64)m * S + s];
         mirna += q;
         uniq += seg_u[(u64)m * S + s];
     }
-    i64 *t = lib_totals + (u64)s * 12;
-    for (int c = 0; c < 12; c++) { t[c] = seg_q[(u64)(n_mir + c) * S + s]; uniq += seg_u[(u64)(n_mir + c) * S + s]; }
-    t[TOT_MIRNA] = mirna;
-    t[TOT_UNIQ] = uniq;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        uniq += __shfl_down_sync(0xffffffffu, uniq, d);
+        mirna += __shfl_down_sync(0xffffffffu, mirna, d);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = uniq; red[1][threadIdx.x >> 5] = mirna; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uniq = 0; mirna = 0;
+        for (int w = 0; w < 8; w++) { uniq += red[0][w]; mirna += red[1][w]; }
+        i64 *t = lib_totals + (u64)s * 12;
+        for (int c = 0; c < 12; c++) { t[c] = seg_q[(u64)(n_mir + c) * S + s]; uniq += seg_u[(u64)(n_mir + c) * S + s]; }
+        t[TOT_MIRNA] = mirna;
+        t[TOT_UNIQ] = uniq;
+    }
 }
