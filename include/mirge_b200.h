@@ -79,8 +79,10 @@ int mirge_detect_phred(const char *fastq, uint64_t nbytes);
  * chunk of FASTQ text (4-line records) of sample `sample`:  H2D copy, parse and
  * 2-bit pack (K0), then 3' quality trim, 3' adapter removal, length filter and
  * insertion into the device hash table of unique sequences (K1).  No trimmed
- * FASTQ is written.  Asynchronous on the context's stream; `fastq` must stay
- * valid until mirge_sync() unless it is pageable memory. */
+ * FASTQ is written.  The text is cut into 64 MiB regions whose H2D copies are
+ * all queued up front, so transfers overlap the kernels of earlier regions
+ * (pinned memory for true overlap).  All copies have completed when the call
+ * returns; the last region's kernels may still be running (mirge_sync). */
 int mirge_feed_fastq(mirge_ctx *ctx, int sample, const char *fastq, uint64_t nbytes, int phred_base);
 /* Same, FASTQ text already resident in device memory (16-byte aligned). */
 int mirge_feed_fastq_device(mirge_ctx *ctx, int sample, const void *fastq_dev, uint64_t nbytes, int phred_base);

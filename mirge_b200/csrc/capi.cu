@@ -504,18 +504,25 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
         if ((u64)k > total) continue;
         const u64 nb = 1ull << (2 * k);
         u32 *boff = nullptr, *cursor = nullptr, *pos = nullptr, *scratch = nullptr;
-        CK(cudaMalloc(&boff, (nb + 1) * sizeof(u32)));
-        CK(cudaMalloc(&cursor, (nb + 1) * sizeof(u32)));
-        CK(cudaMalloc(&pos, (total + 1) * sizeof(u32)));
-        CK(cudaMalloc(&scratch, scan_scratch_elems(nb + 1) * sizeof(u32)));
-        CK(cudaMemsetAsync(boff, 0, (nb + 1) * sizeof(u32), st));
-        const int grid = grid_for(total, 256, 148 * 8);
-        k2_kmer_pass<<<grid, 256, 0, st>>>(L, k, 0, boff, nullptr);
-        device_excl_scan(boff, boff, nb + 1, scratch, st);
-        CK(cudaMemcpyAsync(cursor, boff, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-        k2_kmer_pass<<<grid, 256, 0, st>>>(L, k, 1, cursor, pos);
-        CK(cudaStreamSynchronize(st));
+        cudaError_t e = cudaMalloc(&boff, (nb + 1) * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMalloc(&cursor, (nb + 1) * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMalloc(&pos, (total + 1) * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMalloc(&scratch, scan_scratch_elems(nb + 1) * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMemsetAsync(boff, 0, (nb + 1) * sizeof(u32), st);
+        if (e == cudaSuccess) {
+            const int grid = grid_for(total, 256, 148 * 8);
+            k2_kmer_pass<<<grid, 256, 0, st>>>(L, k, 0, boff, nullptr);
+            device_excl_scan(boff, boff, nb + 1, scratch, st);
+            e = cudaMemcpyAsync(cursor, boff, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) k2_kmer_pass<<<grid, 256, 0, st>>>(L, k, 1, cursor, pos);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
         cudaFree(cursor); cudaFree(scratch);
+        if (e != cudaSuccess) {
+            cudaFree(boff); cudaFree(pos); cudaFree(d_ascii);
+            ctx->err = std::string("seed table build failed: ") + cudaGetErrorString(e);
+            return MIRGE_E_CUDA;
+        }
         const int t = l.ntabs++;
         l.tab_k[t] = k; l.tab_off[t] = boff; l.tab_pos[t] = pos;
     }

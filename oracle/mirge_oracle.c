@@ -414,6 +414,13 @@ int orc_set_adapter(OrcCtx *c, const char *spec)
     return 0;
 }
 
+/* Test knob: the constants trim_file.py hard-codes (:30,:32,:33) and cutadapt's min_overlap default. */
+void orc_set_trim_params(OrcCtx *c, double error_rate, int min_overlap, int min_length, int qcut)
+{
+    c->trim.error_rate = error_rate; c->trim.min_overlap = min_overlap;
+    c->trim.min_length = min_length; c->trim.qcut = qcut;
+}
+
 /* trim_file.py:104-109 -- workers are constructed at index 0, so the quality
  * base they use is decided by read #0 alone: 64 iff it has a char > 'J'. */
 int orc_detect_phred(const char *buf, uint64_t n)

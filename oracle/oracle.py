@@ -50,6 +50,7 @@ def lib():
         L.orc_feed_fastq.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_int, C.c_int]
         L.orc_trim_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_reset.argtypes = [C.c_void_p]
+        L.orc_set_trim_params.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
         L.orc_n_unique.restype = C.c_uint64
         L.orc_n_unique.argtypes = [C.c_void_p]
         L.orc_seq_bytes.restype = C.c_uint64
@@ -167,6 +168,9 @@ class Oracle:
 
     def reset(self):
         lib().orc_reset(self.h)
+
+    def set_trim_params(self, error_rate=0.12, min_overlap=3, min_length=16, qual_cutoff=10):
+        lib().orc_set_trim_params(self.h, error_rate, min_overlap, min_length, qual_cutoff)
 
     def set_adapter(self, spec):
         self._check(lib().orc_set_adapter(self.h, spec.encode()))

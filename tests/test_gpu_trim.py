@@ -57,6 +57,8 @@ def adversarial_reads(rng, adapter, n, maxlen=64, alphabet='ACGT'):
 def _tables(O, reads_fq, adapter, max_read_len=64, force_slow=False, literal=False, **kw):
     from mirge_b200.engine import Engine
     o = O.Oracle(1, False, adapter)
+    if kw:
+        o.set_trim_params(**kw)
     o.feed_fastq(0, reads_fq, 33)
     oe = o.export()
     want = {s: int(c[0]) for s, c in zip(oe['seqs'], oe['counts'])}
@@ -126,3 +128,16 @@ def test_phred64_base(oracle_mod):
     assert e.feed_fastq(0, fq) == base
     oe, ee = o.export(), e.export_unique()
     assert {s: int(c[0]) for s, c in zip(oe['seqs'], oe['counts'])} == {s.decode(): int(c[0]) for s, c in zip(ee['seq'], ee['counts'])}
+
+
+@pytest.mark.parametrize('kw', [dict(error_rate=0.0), dict(error_rate=0.2, min_overlap=1), dict(error_rate=0.34, min_overlap=5),
+                                dict(error_rate=0.12, min_overlap=3, min_length=1, qual_cutoff=20)])
+def test_non_default_trim_parameters(oracle_mod, kw):
+    """error rate / min overlap / min length / quality cutoff are constants in the reference; the kernels take them as parameters."""
+    rng = np.random.default_rng(13)
+    reads = adversarial_reads(rng, ILLUMINA, 30000)
+    quals = [''.join(rng.choice(list('#,5I'), len(r), p=[.1, .1, .2, .6])) for r in reads]
+    fq = _fastq(reads, quals)
+    for mode in (dict(), dict(force_slow=True), dict(force_slow=True, literal=True)):
+        want, got, _, _ = _tables(oracle_mod, fq, ILLUMINA, **mode, **kw)
+        assert got == want, (kw, mode)
