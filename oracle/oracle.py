@@ -64,6 +64,7 @@ def lib():
         L.orc_quality_trim_index.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_locate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.orc_locate_unbanded.argtypes = L.orc_locate.argtypes
+        L.orc_match_back.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_map_one.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_map_bruteforce.argtypes = L.orc_map_one.argtypes
         _LIB = L
@@ -91,6 +92,14 @@ def locate(adapter, read, max_error_rate=0.12, min_overlap=3, banded=True):
     f = lib().orc_locate if banded else lib().orc_locate_unbanded
     ok = f(a, len(a), r, len(r), max_error_rate, min_overlap, _p(out))
     return tuple(int(x) for x in out) if ok else None
+
+
+def match_back(adapter, read, max_error_rate=0.12, min_overlap=3):
+    """Adapter.match_to for a 3' adapter: (rstart, matches) or None (exact str.find first, else locate)."""
+    out = np.zeros(2, np.int32)
+    a, r = adapter.encode(), read.encode()
+    ok = lib().orc_match_back(a, len(a), r, len(r), max_error_rate, min_overlap, _p(out[0:1]), _p(out[1:2]))
+    return (int(out[0]), int(out[1])) if ok else None
 
 
 def py_locate(adapter, read, max_error_rate=0.12, min_overlap=3):

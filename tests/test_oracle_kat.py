@@ -89,6 +89,27 @@ def test_c_python_and_unbanded_locate_agree(oracle_mod):
         assert c == oracle_mod.locate(a, read, banded=False)   # the Ukkonen band is only an optimisation
 
 
+def test_cutadapt_user_guide_examples(oracle_mod):
+    """The 3' adapter table of the cutadapt user guide ("Adapter types", -a ADAPTER), recalled from the
+    published documentation (the docs are not in this image): full adapter anywhere, full adapter at the
+    3' end and a partial adapter at the 3' end are removed with everything after them; with the default
+    10 % error rate a 7-letter adapter tolerates no error."""
+    O = oracle_mod
+
+    def trimmed(read, rate=0.1, overlap=3):
+        m = O.match_back('ADAPTER', read, rate, overlap)
+        return read if m is None else read[:m[0]]
+    assert trimmed('MYSEQUENCEADAPTERSOMETHINGELSE') == 'MYSEQUENCE'
+    assert trimmed('MYSEQUENCEADAPTER') == 'MYSEQUENCE'
+    assert trimmed('MYSEQUENCEADAP') == 'MYSEQUENCE'
+    assert trimmed('ADAPTERSOMETHING') == ''
+    assert trimmed('MYSEQUENCEAD') == 'MYSEQUENCEAD'            # overlap 2 < minimum overlap 3
+    assert trimmed('MYSEQUENCEAD', overlap=2) == 'MYSEQUENCE'
+    assert trimmed('MYSEQUENCEADABTER') == 'MYSEQUENCEADABTER'  # one error in 7 letters: 1 > 0.1 * 7
+    assert trimmed('MYSEQUENCEADABTER', rate=0.2) == 'MYSEQUENCE'
+    assert trimmed('MYSEQUENCE') == 'MYSEQUENCE'
+
+
 # -- bowtie acceptance rules ---------------------------------------------------
 def _lib_oracle(O, seqs, lib_id=0):
     o = O.Oracle(1, False, 'none')
