@@ -160,7 +160,7 @@ def algorithmic_bytes(kernel, n_reads, kept, n_unique, text_bytes, rounds_proces
         return text_bytes + 28 * n_reads + 20 * n_reads
     if kernel in ('k0_count_newlines', 'k0_line_starts'):
         return text_bytes + (16 * n_reads if kernel == 'k0_line_starts' else 0)
-    if kernel == 'k2_round':
+    if kernel.startswith('k2_round'):
         return 130 * rounds_processed
     return None
 
@@ -248,6 +248,7 @@ def run_ours(args):
     # size-independent correctness properties at full size (tests/ hold the bit-exact oracle comparisons)
     p, k, U = eng.stats()
     slow_frac = eng.slow_reads() / float(n_reads)
+    cls = eng.trim_classes()
     tabs = eng.export_tables()
     if N > 1:
         tabs = mdist.reduce_tables({kk: tabs[kk] for kk in ('lib_totals',)}, dev)
@@ -273,7 +274,7 @@ def run_ours(args):
         fam = {n: v for n, v in prof.items() if n.startswith('k') and v[1] > 0}
         dom = max(fam, key=lambda n: fam[n][0])
         dom_ms, dom_n = fam[dom]
-        rounds_proc = int(tabs.get('round_processed', eng.export_tables()['round_processed']).sum()) if dom == 'k2_round' else 0
+        rounds_proc = int(eng.export_tables()['round_processed'][int(dom[len('k2_round')])]) if dom.startswith('k2_round') else 0
         ab = algorithmic_bytes(dom, n_reads, int(k[sample]), U, nbytes, rounds_proc)
         per_launch_bytes = ab * args.steps / dom_n if ab else None
         per_launch_ms = dom_ms / dom_n
@@ -292,7 +293,7 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': 'reads/s', 'n_gpus': N, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u8/u64 (2-bit packed integer)', 'data': 'synthetic',
-            'config': {'workload': workload_name(args), 'reads_per_gpu': n_reads, 'unique_per_gpu': U, 'kept_frac': float(k[sample]) / n_reads, 'k1_slow_path_frac': slow_frac,
+            'config': {'workload': workload_name(args), 'reads_per_gpu': n_reads, 'unique_per_gpu': U, 'kept_frac': float(k[sample]) / n_reads, 'k1_slow_path_frac': slow_frac, 'k1_class1_frac': cls[1] / float(n_reads), 'k1_class2_frac': cls[2] / float(n_reads),
                        'l2_policy': 'inputs (%.2f GB FASTQ text per GPU) larger than the 126 MB L2' % (nbytes / 1e9),
                        'parallelism': 'reads sharded by sample across %d GPU(s); hash-partition all-to-all + table all-reduce' % N},
             'e2e': {'value': e2e, 'unit': 'reads/s', 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},

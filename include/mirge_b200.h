@@ -152,11 +152,16 @@ int mirge_profile_enable(mirge_ctx *ctx, int on);
 /* ms[k], launches[k] accumulated since enable; names[k] static strings. */
 int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const char **names);
 /* Test hook: force_slow = 1 sends every read through the slow queue (all-column
- * bit-vector search), 3 through the literal banded cutadapt DP, 0 restores the
- * windowed fast path, -1 leaves the setting unchanged; slow_reads (may be NULL)
- * receives the number of reads that went through the slow queue so far.
+ * bit-vector search), 3 through the literal banded cutadapt DP, 4 switches the
+ * exact-match prefilter off (every read takes the windowed bit-vector search),
+ * 0 restores the default, -1 leaves the setting unchanged; slow_reads (may be
+ * NULL) receives the number of reads that went through the slow queue so far.
  * Results are identical in every mode. */
 int mirge_debug(mirge_ctx *ctx, int force_slow, uint64_t *slow_reads);
+/* Diagnostics of the trim kernel since the last reset: out3 = reads through the
+ * all-column search, reads the prefilter sent to the full-candidate scan
+ * (class 1), reads it sent to the general search (class 2).  Synchronises. */
+int mirge_trim_classes(mirge_ctx *ctx, uint64_t *out3);
 /* Number of kernels this library has launched on the context so far. */
 uint64_t mirge_launch_count(const mirge_ctx *ctx);
 

@@ -57,6 +57,7 @@ struct mirge_ctx {
     // trim configuration
     TrimParams tp;
     K1Thr thr;
+    K1Pre pre;
     int qual_cutoff = 10;
     int force_slow = 0;
     // K0 scratch
@@ -70,7 +71,7 @@ struct mirge_ctx {
     u64 max_unique = 0;
     u64 *d_useq = nullptr, *d_unmask = nullptr; u8 *d_ulen = nullptr; u32 *d_counts = nullptr;
     signed char *d_round_of = nullptr, *d_mm_of = nullptr; int *d_ref_of = nullptr, *d_pos_of = nullptr;
-    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept, [2+S] slow-path reads
+    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept, [2+S..5+S) K1 diagnostics (all-column search, class 1, class 2)
     u64 *d_ctr = nullptr;
     u64 *d_len_hist = nullptr;
     std::vector<u64> processed;
@@ -152,6 +153,72 @@ static TableView<W> table_view(mirge_ctx *c)
     return T;
 }
 
+
+// ---------------------------------------------------------------------------
+// K1 prefilter tables (k1_prefilter.cuh).  For the "wildcard read" W^I + A[0..l):
+// G[i][j][c] = most matches any alignment path from row 0 to cell (i, j) can
+// collect with cost <= c (wildcard columns match every adapter base).  A candidate
+// cell can outrank the exact-prefix candidate E only with >= l + 1 matches at a
+// cost within its own threshold thr[i].
+// ---------------------------------------------------------------------------
+static void k1pre_dp(const unsigned char *A, int m, int I, int l, int K, std::vector<short> &G)
+{
+    const int n = I + l;
+    const short NEG = -1000;
+    auto at = [&](int i, int j, int c) -> short & { return G[((size_t)i * (n + 1) + j) * K + c]; };
+    for (int j = 0; j <= n; j++) for (int c = 0; c < K; c++) at(0, j, c) = 0;
+    for (int i = 1; i <= m; i++) for (int c = 0; c < K; c++) at(i, 0, c) = (c >= i) ? 0 : NEG;
+    for (int j = 1; j <= n; j++)
+        for (int i = 1; i <= m; i++)
+            for (int c = 0; c < K; c++) {
+                short best = NEG;
+                const bool eq = (j <= I) || (A[i - 1] == A[j - 1 - I]);
+                if (eq) { short v = at(i - 1, j - 1, c); if (v > NEG && v + 1 > best) best = v + 1; }
+                if (c > 0) {
+                    short v = at(i - 1, j - 1, c - 1); if (v > best) best = v;      // mismatch
+                    v = at(i - 1, j, c - 1); if (v > best) best = v;                // adapter base unmatched
+                    v = at(i, j - 1, c - 1); if (v > best) best = v;                // read base unmatched
+                }
+                at(i, j, c) = best;
+            }
+}
+
+static void k1pre_build(const TrimParams &tp, const K1Thr &thr, K1Pre &pre)
+{
+    memset(&pre, 0, sizeof pre);
+    if (tp.mode != 1 || tp.n_adapters != 1) return;
+    const int m = tp.alen[0];
+    if (m < 8 || m > 32) return;
+    const int kmax = thr.v[m];
+    if (kmax < 0 || m + kmax + 1 > K1PRE_MAXI) return;
+    unsigned char A[32];
+    for (int i = 0; i < m; i++) A[i] = (unsigned char)((tp.aw[0][0] >> (2 * i)) & 3ull);
+    const int K = kmax + 1, icap = m + kmax + 1;
+    std::vector<short> G((size_t)(m + 1) * (icap + m + 1) * K);
+    for (int I = 0; I <= icap; I++) {
+        for (int l = 4; l < m; l++) {
+            if (thr.v[l] < 0) continue;                 // E itself is not an acceptable candidate
+            const int n = I + l;
+            k1pre_dp(A, m, I, l, K, G);
+            auto at = [&](int i, int j, int c) { return G[((size_t)i * (n + 1) + j) * K + c]; };
+            bool partial = false;
+            int reach = -1;
+            for (int i = l + 1; i <= m; i++)
+                if (thr.v[i] >= 0 && at(i, n, thr.v[i]) >= l + 1) partial = true;
+            for (int j = 1; j <= n; j++)
+                if (at(m, j, kmax) >= l + 1) reach = j;
+            if (!partial && reach < 0) pre.safe_len[I] |= 1u << l;
+            if (I == icap) {                             // inserts this long behave like an unbounded one
+                if (!partial) pre.safe_p |= 1u << l;
+                pre.fullreach[l] = (u8)(reach > I ? reach - I : 0);
+            }
+        }
+    }
+    pre.m = m; pre.icap = icap;
+    pre.anchor_rep = (u32)(tp.aw[0][0] & 0xFFull) * 0x01010101u;
+    pre.enabled = 1;
+}
+
 // Definitions below take C linkage from their declarations in mirge_b200.h.
 
 const char *mirge_last_error(const mirge_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -170,6 +237,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     ctx->max_unique = max_unique;
     ctx->processed.assign(n_samples, 0);
     memset(&ctx->tp, 0, sizeof ctx->tp);
+    memset(&ctx->pre, 0, sizeof ctx->pre);
     ctx->tp.mode = 0; ctx->tp.error_rate = 0.12; ctx->tp.min_overlap = 3; ctx->tp.min_length = 16;
     memset(ctx->prof_ms, 0, sizeof ctx->prof_ms); memset(ctx->prof_n, 0, sizeof ctx->prof_n);
     CK(cudaSetDevice(device));
@@ -188,7 +256,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_mm_of, max_unique));
     CK(cudaMalloc(&ctx->d_ref_of, max_unique * sizeof(int)));
     CK(cudaMalloc(&ctx->d_pos_of, max_unique * sizeof(int)));
-    CK(cudaMalloc(&ctx->d_ctr, (3 + (size_t)n_samples) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_ctr, (5 + (size_t)n_samples) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_len_hist, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_todo[0], max_unique * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_todo[1], max_unique * sizeof(u32)));
@@ -198,7 +266,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_lib_totals, (size_t)n_samples * MIRGE_N_TOTALS * sizeof(i64)));
     CK(cudaMemsetAsync(ctx->d_slots, 0, cap * esz, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counts, 0, max_unique * (size_t)n_samples * sizeof(u32), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_ctr, 0, (3 + (size_t)n_samples) * sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (5 + (size_t)n_samples) * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -295,6 +363,7 @@ int mirge_set_adapter(mirge_ctx *ctx, const char *spec, double error_rate, int m
         if (i >= min_overlap) { c = 0; while ((double)(c + 1) <= (double)i * error_rate) c++; }
         ctx->thr.v[i] = (signed char)c;
     }
+    k1pre_build(ctx->tp, ctx->thr, ctx->pre);
     ctx->qual_cutoff = qual_cutoff;
     return MIRGE_OK;
 }
@@ -395,7 +464,7 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
                                                                        ctx->d_meta, (u32 *)(ctx->d_ctr + 1)); }
             { ProfScope ps(ctx, KID_K1_TRIM);
               k1_trim_collapse<W><<<grid_for(nrec, K1_THREADS, 148 * 16), K1_THREADS, 0, st>>>(
-                  ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->thr, table_view<W>(ctx), kc, ctx->force_slow); }
+                  ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->thr, ctx->pre, table_view<W>(ctx), kc, ctx->force_slow); }
         }
         // carry the pending line starts to the front for the next region
         const u32 q2 = (u32)(lines % 4);
@@ -773,7 +842,7 @@ int mirge_reset(mirge_ctx *ctx)
     int rc = mirge_reset_unique(ctx);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_ctr, 0, (3 + (size_t)ctx->S) * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (5 + (size_t)ctx->S) * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * ctx->S * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), st));
     ctx->processed.assign(ctx->S, 0);
@@ -790,6 +859,14 @@ int mirge_debug(mirge_ctx *ctx, int force_slow, uint64_t *slow_reads)
         if (rc) return rc;
         CK(cudaMemcpy(slow_reads, ctx->d_ctr + 2 + ctx->S, sizeof(u64), cudaMemcpyDeviceToHost));
     }
+    return MIRGE_OK;
+}
+
+int mirge_trim_classes(mirge_ctx *ctx, uint64_t *out3)
+{
+    int rc = mirge_sync(ctx);
+    if (rc) return rc;
+    CK(cudaMemcpy(out3, ctx->d_ctr + 2 + ctx->S, 3 * sizeof(u64), cudaMemcpyDeviceToHost));
     return MIRGE_OK;
 }
 

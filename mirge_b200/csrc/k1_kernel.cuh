@@ -21,6 +21,7 @@
 #pragma once
 #include "common.cuh"
 #include "k1_trim.cuh"
+#include "k1_prefilter.cuh"
 
 #define K1_THREADS 128
 #define K1_RING 8
@@ -28,7 +29,7 @@
 struct K1Counters {
     u64 *kept;        // [S]
     u64 *len_hist;    // [(max_len + 1)][S]
-    u64 *slow_reads;  // diagnostic: reads that took the slow path
+    u64 *slow_reads;  // diagnostics: [0] reads through the all-column search, [1] class-1 reads, [2] class-2 reads
 };
 
 // thr[i] = largest cost c with c <= i * error_rate (double), or -1 below min_overlap
@@ -105,6 +106,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
             }
         }
         const int jend = (nmax - j0) < 16 ? (nmax - j0) : 16;
+        u32 le16 = 0, z16 = 0;                     // bit t: cost(m, j0+t+1) <= thr_m / == 0
 #pragma unroll 4
         for (int t = 0; t < jend; t++) {
             const int j = j0 + t + 1;
@@ -119,16 +121,23 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
                 Ph <<= 1; Mh <<= 1;
                 Pv = Mh | ~(Xv | Ph);
                 Mv = Ph & Xv;
+                le16 |= (u32)(score <= thr_m) << t;
+                z16 |= (u32)(score == 0) << t;
                 if (j >= win_lo) {
                     const int slot = (j & (K1_RING - 1)) * K1_THREADS;
                     ring[slot] = (u64)Pv | ((u64)Mv << 32);
                     ringh[slot] = Mh;
-                    if (score <= thr_m) full_mask |= 1u << (j - win_lo);
-                } else if (score <= thr_m) {
-                    slow = true;           // inexact full-length occurrence far from the read end: literal DP decides
                 }
-                if (score == 0 && exact_j < 0) exact_j = j;          // str.find: leftmost exact occurrence
             }
+        }
+        // once per 16 columns: leftmost exact occurrence (str.find), full-length candidates
+        // inside the window, and inexact full-length occurrences far from the read end
+        if (z16 && exact_j < 0) exact_j = j0 + __ffs(z16);
+        if (le16) {
+            int below = win_lo - 1 - j0;           // columns of this chunk that lie before the window
+            below = below < 0 ? 0 : (below > 16 ? 16 : below);
+            if (le16 & ((1u << below) - 1u)) slow = true;
+            if (below < 16) full_mask |= (le16 >> below) << (j0 + below + 1 - win_lo);
         }
     }
     // cutadapt keeps the candidate with most matches, then lowest cost, then first
@@ -384,72 +393,152 @@ __device__ __forceinline__ bool k1_finish(PSeq<W> &p, int n, const TrimParams &t
     return true;
 }
 
-// force_slow != 0 routes every read through the literal DP (parity tests).
+// Reads queued by one warp for a later, fully converged pass.
+#define K1_Q1 64      // class 1: full-candidate scan
+#define K1_Q2 128     // class 2: windowed bit-vector search with candidate walks
+#define K1_Q3 128     // reads the windowed search could not settle
+
+// force_slow bits (parity tests): 1 = every read through the all-column search,
+// 2 = ... through the literal DP instead, 4 = prefilter off.
 template <int W>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-                 u64 n_records, int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, int force_slow)
+                 u64 n_records, int sample, TrimParams tp_param, K1Thr thr_param, K1Pre pre_param, TableView<W> T, K1Counters ctr,
+                 int force_slow)
 {
     __shared__ u64 ring[K1_RING * K1_THREADS];
     __shared__ u32 ringh[K1_RING * K1_THREADS];
-    __shared__ u32 slowq[K1_THREADS / 32][64];     // one queue per warp: no CTA-wide barrier in the main loop
+    __shared__ u32 q1r[K1_THREADS / 32][K1_Q1];     // one set of queues per warp: no CTA-wide barrier in the main loop
+    __shared__ u16 q1i[K1_THREADS / 32][K1_Q1];     // rstart | limit << 8
+    __shared__ u32 q2[K1_THREADS / 32][K1_Q2];
+    __shared__ u32 q3[K1_THREADS / 32][K1_Q3];
     __shared__ u32 sh_hist[32 * W + 1];
     __shared__ TrimParams tp;                       // dynamic indexing by adapter: keep it out of local memory
+    __shared__ K1Pre pre;
     __shared__ signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
     __shared__ u32 peq8[MIRGE_MAX_ADAPTERS * 8];
     for (int b = threadIdx.x; b <= 32 * W; b += K1_THREADS) sh_hist[b] = 0;
     for (int b = threadIdx.x; b <= MIRGE_MAX_ADAPTER_LEN; b += K1_THREADS) thr[b] = thr_param.v[b];
     for (int b = threadIdx.x; b < (int)(sizeof(TrimParams) / 4); b += K1_THREADS)
         reinterpret_cast<u32 *>(&tp)[b] = reinterpret_cast<const u32 *>(&tp_param)[b];
+    for (int b = threadIdx.x; b < (int)(sizeof(K1Pre) / 4); b += K1_THREADS)
+        reinterpret_cast<u32 *>(&pre)[b] = reinterpret_cast<const u32 *>(&pre_param)[b];
     if (threadIdx.x < MIRGE_MAX_ADAPTERS * 8)
         peq8[threadIdx.x] = (threadIdx.x & 4) ? 0u : (u32)tp_param.peq[threadIdx.x >> 3][threadIdx.x & 3];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    u32 qn = 0;                                     // entries in this warp's queue (warp-uniform)
-    u32 my_kept = 0, my_slow = 0;
+    const unsigned below = (1u << lane) - 1u;
+    const bool use_pre = pre.enabled && !(force_slow & 4);
+    const u64 aw0 = tp.aw[0][0];
+    const int thr_m0 = thr[tp.alen[0]];
+    u32 n1 = 0, n2 = 0, n3 = 0;                     // queue fills (warp-uniform)
+    u32 my_kept = 0, my_slow = 0, my_c1 = 0, my_c2 = 0;
     u64 *my_ring = ring + threadIdx.x;
     u32 *my_ringh = ringh + threadIdx.x;
     for (u64 r0 = (u64)blockIdx.x * K1_THREADS; r0 < n_records; r0 += (u64)gridDim.x * K1_THREADS) {
         const u64 r = r0 + threadIdx.x;
         const bool live = r < n_records;
-        PSeq<W> p;
-        int n = 0;
-        if (live) k1_load_record<W>(bases, nmask, meta, r, p, n);
-        else {
+        {
+            PSeq<W> p;
+            int n = 0;
+            if (live) k1_load_record<W>(bases, nmask, meta, r, p, n);
+            else {
 #pragma unroll
-            for (int w = 0; w < W; w++) p.s[w] = 0;
+                for (int w = 0; w < W; w++) p.s[w] = 0;
 #pragma unroll
-            for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
-        }
-        int nf = n;
-        if (tp.mode == 2) {
-            const int L = tp.uncond;
-            if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); nf = n - cut; }
-            else if (L < 0) { const int cut = (-L) < n ? (-L) : n; nf = n - cut; }
-        } else if (tp.mode == 1) {
-            nf = (force_slow & 3) ? K1_SLOW : k1_trim_fast<W>(p, n, tp, thr, my_ring, my_ringh, peq8);   // warp-uniform branch
+                for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
+            }
+            int nf = n, cls = 0, lim = 0;
+            if (tp.mode == 2) {
+                const int L = tp.uncond;
+                if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); nf = n - cut; }
+                else if (L < 0) { const int cut = (-L) < n ? (-L) : n; nf = n - cut; }
+            } else if (tp.mode == 1) {
+                if (force_slow & 3) cls = 3;
+                else if (use_pre) cls = k1_prefilter<W>(p, n, pre, aw0, nf, lim);
+                else cls = 2;
+            }
+            if (!live) cls = -1;
+            const unsigned b1 = __ballot_sync(0xffffffffu, cls == 1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, cls == 2);
+            const unsigned b3 = __ballot_sync(0xffffffffu, cls == 3);
+            if (cls == 1) {
+                const u32 at = n1 + __popc(b1 & below);
+                q1r[wid][at] = (u32)r; q1i[wid][at] = (u16)(nf | (lim << 8));
+                my_c1++;
+            } else if (cls == 2) {
+                q2[wid][n2 + __popc(b2 & below)] = (u32)r;
+                my_c2++;
+            } else if (cls == 3) {
+                q3[wid][n3 + __popc(b3 & below)] = (u32)r;
+            }
+            n1 += __popc(b1); n2 += __popc(b2); n3 += __popc(b3);
+            if (cls == 0) my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
         }
         __syncwarp();
-        {   // queue the reads the windowed search could not settle
-            const unsigned sm = __ballot_sync(0xffffffffu, live && nf == K1_SLOW);
-            if (live && nf == K1_SLOW) slowq[wid][qn + __popc(sm & ((1u << lane) - 1u))] = (u32)r;
-            qn += __popc(sm);
-        }
-        if (live && nf != K1_SLOW) my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
-        __syncwarp();
-        // drain 32 at a time (a full warp of slow reads), and whatever is left after the last tile
+        // drain full warps of queued reads, and whatever is left after the last tile
         const bool last_tile = r0 + (u64)gridDim.x * K1_THREADS >= n_records;
-        while (qn >= 32 || (last_tile && qn > 0)) {
-            const u32 take = qn < 32 ? qn : 32;
+        while (n1 >= 32 || (last_tile && n1 > 0)) {
+            const u32 take = n1 < 32 ? n1 : 32;
+            const bool on = lane < take;
+            PSeq<W> ps;
+            int ns = 0, lim = 0, rs = 0;
+            u32 rr = 0;
+            if (on) {
+                rr = q1r[wid][n1 - take + lane];
+                const u32 info = q1i[wid][n1 - take + lane];
+                rs = info & 0xFF; lim = info >> 8;
+                k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; w++) ps.s[w] = 0;
+#pragma unroll
+                for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
+            }
+            const bool hit = k1_full_candidate_scan<W>(ps, lim, tp.alen[0], thr_m0, peq8);
+            n1 -= take;
+            __syncwarp();
+            const unsigned hb = __ballot_sync(0xffffffffu, on && hit);
+            if (on && hit) q2[wid][n2 + __popc(hb & below)] = rr;       // a full-length candidate: general search decides
+            n2 += __popc(hb);
+            if (on && !hit) my_kept += k1_finish<W>(ps, rs, tp, T, sample, sh_hist) ? 1u : 0u;
+            __syncwarp();
+        }
+        while (n2 >= 32 || (last_tile && n2 > 0)) {
+            const u32 take = n2 < 32 ? n2 : 32;
+            const bool on = lane < take;
+            PSeq<W> ps;
+            int ns = 0;
+            u32 rr = 0;
+            if (on) {
+                rr = q2[wid][n2 - take + lane];
+                k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; w++) ps.s[w] = 0;
+#pragma unroll
+                for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
+            }
+            const int nfs = k1_trim_fast<W>(ps, ns, tp, thr, my_ring, my_ringh, peq8);       // warp-collective
+            n2 -= take;
+            __syncwarp();
+            const unsigned sb = __ballot_sync(0xffffffffu, on && nfs == K1_SLOW);
+            if (on && nfs == K1_SLOW) q3[wid][n3 + __popc(sb & below)] = rr;
+            n3 += __popc(sb);
+            if (on && nfs != K1_SLOW) my_kept += k1_finish<W>(ps, nfs, tp, T, sample, sh_hist) ? 1u : 0u;
+            __syncwarp();
+        }
+        while (n3 >= 32 || (last_tile && n3 > 0)) {
+            const u32 take = n3 < 32 ? n3 : 32;
             if (lane < take) {
                 PSeq<W> ps;
                 int ns;
-                k1_load_record<W>(bases, nmask, meta, (u64)slowq[wid][qn - take + lane], ps, ns);
+                k1_load_record<W>(bases, nmask, meta, (u64)q3[wid][n3 - take + lane], ps, ns);
                 const int nfs = k1_trim_slow<W>(ps, ns, tp, thr, peq8, (force_slow & 2) != 0);
                 my_kept += k1_finish<W>(ps, nfs, tp, T, sample, sh_hist) ? 1u : 0u;
                 my_slow++;
             }
-            qn -= take;
+            n3 -= take;
             __syncwarp();
         }
     }
@@ -457,10 +546,16 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
     for (int d = 16; d > 0; d >>= 1) {
         my_kept += __shfl_down_sync(0xffffffffu, my_kept, d);
         my_slow += __shfl_down_sync(0xffffffffu, my_slow, d);
+        my_c1 += __shfl_down_sync(0xffffffffu, my_c1, d);
+        my_c2 += __shfl_down_sync(0xffffffffu, my_c2, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (my_kept) atomicAdd(&ctr.kept[sample], (u64)my_kept);
-        if (my_slow && ctr.slow_reads) atomicAdd(ctr.slow_reads, (u64)my_slow);
+        if (ctr.slow_reads) {
+            if (my_slow) atomicAdd(ctr.slow_reads, (u64)my_slow);
+            if (my_c1) atomicAdd(ctr.slow_reads + 1, (u64)my_c1);
+            if (my_c2) atomicAdd(ctr.slow_reads + 2, (u64)my_c2);
+        }
     }
     __syncthreads();
     for (int b = threadIdx.x; b <= 32 * W; b += K1_THREADS)

@@ -1,0 +1,158 @@
+// k1_prefilter.cuh -- settles most reads without any dynamic programming.
+//
+// cutadapt's Adapter.match_to (adapters.py, where = BACK) returns the leftmost exact
+// occurrence of the whole adapter when there is one (str.find), and otherwise ranks the
+// candidate end cells of Aligner.locate (_align.pyx) by (matches, cost, first visited).
+// For the reads sequencers actually produce the answer is decided by EXACT comparisons:
+//
+//   FULL  the whole adapter occurs exactly            -> rstart = leftmost occurrence
+//   E     no FULL, and the read ends with an exact adapter prefix A[0..l), l < m
+//         (take the longest).  E is itself a candidate: cell (l, n), cost 0,
+//         matches l, origin n - l.  Any candidate X that outranks it needs
+//         matches(X) >= l + 1 (same matches means cost > 0, or X = E).
+//
+// Whether such an X can exist is bounded on the host once per adapter
+// (capi.cu:k1pre_build) with a dynamic program over the "wildcard read" W^I + A[0..l)
+// -- I = n - l insert bases that match anything, then the exact prefix -- which
+// maximises the matches of every alignment path whose cost stays within the
+// candidate's threshold.  Any path in a real read maps to a path of the wildcard
+// read with cost <= and matches >=, so when the wildcard read admits no X, no real
+// read with that (I, l) does:
+//
+//   safe_len[I] bit l   no X at all                      -> class 0: rstart = n - l
+//   safe_p bit l        no X among the adapter prefixes at the read end, whatever
+//                       the insert; full-length X must end at a column
+//                       <= I + fullreach[l]             -> class 1: the read only
+//                       needs the bit-vector cost scan of those columns (no
+//                       candidate walks); no full-length candidate there -> rstart = n - l
+//   otherwise                                            -> class 2: general search
+//
+// The search for FULL / E uses the adapter's first four bases as an anchor: all anchor
+// occurrences are found with byte-wise SIMD-in-register compares of the 2-bit words at the
+// four base phases, then each occurrence is extended with one XOR of a 64-bit window.
+#pragma once
+#include "common.cuh"
+
+#define K1PRE_MAXI 48
+
+struct K1Pre {
+    int enabled;                      // single adapter, 8 <= m <= 32, tables built
+    int m;
+    int icap;                         // safe_len is defined for I <= icap (larger inserts: never safe by length)
+    u32 anchor_rep;                   // A[0..4) packed in one byte, replicated
+    u32 safe_p;
+    u32 safe_len[K1PRE_MAXI + 1];
+    u8 fullreach[32];
+};
+
+// Returns the class (0, 1, 2).  Class 0/1: rstart = start of FULL / E.  Class 1: limit =
+// last column whose full-length cost must be checked.
+template <int W>
+__device__ __forceinline__ int k1_prefilter(const PSeq<W> &p, int n, const K1Pre &pre, u64 aw, int &rstart, int &limit)
+{
+    constexpr int NW = 2 * W;
+    u32 w[NW + 1];
+#pragma unroll
+    for (int k = 0; k < W; k++) { w[2 * k] = (u32)p.s[k]; w[2 * k + 1] = (u32)(p.s[k] >> 32); }
+    w[NW] = 0;
+    u32 c[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) c[k] = 0;
+    const u32 rep = pre.anchor_rep;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const u32 y = r ? __funnelshift_r(w[k], w[k + 1], 2 * r) : w[k];
+            const u32 x = y ^ rep;
+            const u32 z = (x - 0x01010101u) & ~x & 0x80808080u;      // zero bytes (may over-report; every hit is verified)
+            c[k] |= z >> (7 - 2 * r);                                 // occurrence at base 16k + 4b + r -> bit 8b + 2r
+        }
+    }
+    // occurrences must leave room for the four anchor bases: positions <= n - 4
+    const int V = n - 3;
+    u64 cc[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        u64 v = (u64)c[2 * k] | ((u64)c[2 * k + 1] << 32);
+        const int lo = 32 * k;
+        if (V <= lo) v = 0;
+        else if (V < lo + 32) v &= (1ull << (2 * (V - lo))) - 1ull;
+        cc[k] = v;
+    }
+    const int m = pre.m;
+    for (;;) {
+        int kk = -1;
+        u64 cur = 0;
+#pragma unroll
+        for (int k = W - 1; k >= 0; k--) if (cc[k]) { kk = k; cur = cc[k]; }
+        if (kk < 0) break;
+        const int b = __ffsll((long long)cur) - 1;
+#pragma unroll
+        for (int k = 0; k < W; k++) if (k == kk) cc[k] &= cc[k] - 1;
+        const int pos = kk * 32 + (b >> 1);
+        const u64 x = words_window64<W>(p.s, pos) ^ aw;
+        u64 mm = (x | (x >> 1)) & 0x5555555555555555ull;
+        const int vl = (n - pos) < m ? (n - pos) : m;
+        if (vl < 32) mm |= 1ull << (2 * vl);
+        int ml = mm ? ((__ffsll((long long)mm) - 1) >> 1) : 32;
+        u32 nb = mask_window32<W / 2>(p.nm, pos);
+        if (ml < 32) nb &= (1u << ml) - 1u;
+        if (nb) ml = __ffs(nb) - 1;
+        if (ml >= m) { rstart = pos; return 0; }                      // FULL: leftmost, occurrences are visited in order
+        if (pos + ml >= n) {                                          // E with l = ml, I = pos
+            rstart = pos;
+            if (pos <= pre.icap && ((pre.safe_len[pos] >> ml) & 1u)) return 0;
+            if ((pre.safe_p >> ml) & 1u) {
+                const int lim = pos + pre.fullreach[ml];
+                limit = lim < n ? lim : n;
+                return 1;
+            }
+            return 2;
+        }
+    }
+    return 2;
+}
+
+// Class 1: does any column j <= limit hold a full-length candidate (cost(m, j) <= thr_m)?
+// Myers' bit-vector column recurrence, score only; warp lock-step (uniform trip count).
+template <int W>
+__device__ __forceinline__ bool k1_full_candidate_scan(const PSeq<W> &p, int limit, int m, int thr_m, const u32 *peq8)
+{
+    u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
+    int score = m;
+    const int top = m - 1;
+    bool hit = false;
+    const int lmax = __reduce_max_sync(0xffffffffu, limit);
+    for (int j0 = 0; j0 < lmax; j0 += 16) {
+        u32 bw = 0, nb = 0;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            if ((j0 >> 5) == w) {
+                bw = (u32)(p.s[w] >> ((j0 & 16) * 2));
+                nb = (u32)(p.nm[w >> 1] >> (((w & 1) * 32) + (j0 & 16))) & 0xFFFFu;
+            }
+        }
+        const int jend = (lmax - j0) < 16 ? (lmax - j0) : 16;
+        u32 le16 = 0;
+#pragma unroll 4
+        for (int t = 0; t < jend; t++) {
+            const u32 Eq = peq8[(bw & 3u) | (((nb >> t) & 1u) << 2)];
+            bw >>= 2;
+            const u32 Xv = Eq | Mv;
+            const u32 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            u32 Ph = Mv | ~(Xh | Pv);
+            u32 Mh = Pv & Xh;
+            score += (int)((Ph >> top) & 1u) - (int)((Mh >> top) & 1u);
+            Ph <<= 1; Mh <<= 1;
+            Pv = Mh | ~(Xv | Ph);
+            Mv = Ph & Xv;
+            le16 |= (u32)(score <= thr_m) << t;
+        }
+        // columns past `limit` ran on padding; drop them
+        const int keep = limit - j0;
+        if (keep < 16) le16 &= keep <= 0 ? 0u : ((1u << keep) - 1u);
+        hit = hit || le16 != 0u;
+    }
+    return hit;
+}

@@ -172,6 +172,16 @@ class Engine:
         (literal=True) the cell-for-cell cutadapt DP."""
         self._ck(lib.mirge_debug(self.h, (3 if literal else 1) if on else 0, None))
 
+    def set_trim_mode(self, mode):
+        """Test hook: raw mirge_debug mode (0 default, 1 all-column search, 3 literal DP, 4 prefilter off)."""
+        self._ck(lib.mirge_debug(self.h, int(mode), None))
+
+    def trim_classes(self):
+        """(reads through the all-column search, prefilter class-1 reads, prefilter class-2 reads)."""
+        n = np.zeros(3, np.uint64)
+        self._ck(lib.mirge_trim_classes(self.h, _ptr(n)))
+        return tuple(int(x) for x in n)
+
     def slow_reads(self):
         n = np.zeros(1, np.uint64)
         self._ck(lib.mirge_debug(self.h, -1, _ptr(n)))

@@ -54,7 +54,7 @@ def adversarial_reads(rng, adapter, n, maxlen=64, alphabet='ACGT'):
     return reads
 
 
-def _tables(O, reads_fq, adapter, max_read_len=64, force_slow=False, literal=False, **kw):
+def _tables(O, reads_fq, adapter, max_read_len=64, force_slow=False, literal=False, mode=None, **kw):
     from mirge_b200.engine import Engine
     o = O.Oracle(1, False, adapter)
     if kw:
@@ -66,6 +66,8 @@ def _tables(O, reads_fq, adapter, max_read_len=64, force_slow=False, literal=Fal
     e.set_adapter(adapter, **kw)
     if force_slow:
         e.force_slow_path(True, literal)
+    if mode is not None:
+        e.set_trim_mode(mode)
     e.feed_fastq(0, reads_fq, 33)
     ee = e.export_unique()
     got = {s.decode(): int(c[0]) for s, c in zip(ee['seq'], ee['counts'])}
@@ -88,6 +90,64 @@ def test_adversarial_reads_fast_and_slow(oracle_mod, adapter):
     assert got2 == want2 and slow2 == n2
     want3, got3, slow3, n3 = _tables(oracle_mod, fq, adapter, force_slow=True, literal=True)  # literal cutadapt DP
     assert got3 == want3 and slow3 == n3
+    want4, got4, _, _ = _tables(oracle_mod, fq, adapter, mode=4)                             # exact-match prefilter off
+    assert got4 == want4
+
+
+def prefilter_reads(rng, adapter, n, maxlen=64):
+    """Reads that end in an EXACT adapter prefix (or hold the whole adapter) behind inserts built from
+    random bases, adapter pieces and edited adapter copies: the shapes the prefilter settles without DP,
+    and the ones that must make it back off."""
+    m = len(adapter)
+    reads = []
+    for _ in range(n):
+        ilen = int(rng.integers(0, maxlen + 1))
+        ins = []
+        kind = int(rng.integers(0, 4))
+        while len(ins) < ilen:
+            mode = 0 if kind == 0 else int(rng.integers(0, 4))
+            if mode == 0:
+                ins.append('ACGT'[rng.integers(0, 4)])
+            elif mode == 1:
+                a = int(rng.integers(0, m)); ins.extend(adapter[a:a + int(rng.integers(1, m + 1))])
+            elif mode == 2:
+                ins.extend(_mutate(rng, adapter[:int(rng.integers(1, m + 1))], int(rng.integers(0, 3)), int(rng.integers(0, 2)), int(rng.integers(0, 2))))
+            else:
+                ins.append(adapter[rng.integers(0, m)])
+        ins = ''.join(ins[:ilen])
+        tail = adapter[:int(rng.integers(0, m + 1))]
+        if rng.random() < 0.15:
+            tail = adapter + ''.join('ACGT'[x] for x in rng.integers(0, 4, int(rng.integers(0, 8))))
+        r = (ins + tail)[:maxlen]
+        if rng.random() < 0.03 and r:
+            q = int(rng.integers(0, len(r))); r = r[:q] + 'N' + r[q + 1:]
+        reads.append(r if r else 'A')
+    return reads
+
+
+@pytest.mark.parametrize('adapter', [ILLUMINA, 'TGGAATTCTCGGGTGCCAAGG', 'AAAAAAAAAAAAAAAA', 'ACACACACACACACACACAC', 'TGGAATTC',
+                                     'AGATCGGAAGAGCACACGTCTGAACTCCAGTC', 'TTTTGGAATTTTGGAATTGGAATT'])
+@pytest.mark.parametrize('maxlen', [50, 64, 128])
+def test_prefilter_classes_match_literal_dp(oracle_mod, adapter, maxlen):
+    rng = np.random.default_rng(len(adapter) * 131 + maxlen)
+    reads = prefilter_reads(rng, adapter, 80000, maxlen)
+    fq = _fastq(reads)
+    mrl = 64 if maxlen <= 64 else 128
+    from mirge_b200.engine import Engine
+    o = oracle_mod.Oracle(1, False, adapter)
+    o.feed_fastq(0, fq, 33)
+    oe = o.export()
+    want = {s: int(c[0]) for s, c in zip(oe['seqs'], oe['counts'])}
+    e = Engine(1, False, 1 << 20, mrl)
+    e.set_adapter(adapter)
+    e.feed_fastq(0, fq, 33)
+    ee = e.export_unique()
+    got = {s.decode(): int(c[0]) for s, c in zip(ee['seq'], ee['counts'])}
+    assert got == want
+    slow, c1, c2 = e.trim_classes()
+    assert c1 + c2 < len(reads)          # some reads are settled by exact comparisons alone
+    if adapter == ILLUMINA:
+        assert c1 > 0 and c1 + c2 < 0.8 * len(reads)
 
 
 def test_long_adapter_and_long_reads(oracle_mod):
