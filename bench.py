@@ -271,7 +271,7 @@ def run_ours(args):
         if os.path.exists(pk_path):
             peaks = json.load(open(pk_path))
         peak = float(peaks.get('hbm_gbs', 6650.0))
-        fam = {n: v for n, v in prof.items() if n.startswith('k') and v[1] > 0}
+        fam = {n: v for n, v in prof.items() if n.startswith('k') and v[1] > 0 and not n.startswith(('k1a', 'k1b', 'k1c', 'k1d'))}   # k1a..k1d are the four launches of the k1_trim_collapse family
         dom = max(fam, key=lambda n: fam[n][0])
         dom_ms, dom_n = fam[dom]
         rounds_proc = int(eng.export_tables()['round_processed'][int(dom[len('k2_round')])]) if dom.startswith('k2_round') else 0

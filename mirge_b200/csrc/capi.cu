@@ -24,14 +24,15 @@ enum KernelId {
     KID_K0_COUNT = 0, KID_K0_SCAN, KID_K0_LINES, KID_K0_PACK, KID_K1_TRIM, KID_K3_KEYS, KID_K3_SORT,
     KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_RESET,
     KID_K2_ROUND0 = 16,   // .. KID_K2_ROUND0 + 9
-    KID_N = 26
+    KID_K1_CLASSIFY = 26, KID_K1_SCAN, KID_K1_GENERAL, KID_K1_SLOW,
+    KID_N = 30
 };
 static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
     "k0_count_newlines", "k0_scan", "k0_line_starts", "k0_pack", "k1_trim_collapse", "k3_make_keys",
     "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "reset_memset", "", "",
     "k2_round0_mirna_exact", "k2_round1_hairpin", "k2_round2_mature_trna", "k2_round3_pre_trna", "k2_round4_snorna",
     "k2_round5_rrna", "k2_round6_ncrna_others", "k2_round7_mrna", "k2_round8_isomir", "k2_round9_spikein",
-    "", "", "", "", "", ""};
+    "k1a_classify_collapse", "k1b_scan_class1", "k1c_general_search", "k1d_slow_search", "", ""};
 
 struct DevLib {
     u64 *seq = nullptr, *amb = nullptr;
@@ -66,6 +67,7 @@ struct mirge_ctx {
     u32 *d_scan = nullptr; size_t scan_cap = 0;
     u32 *d_lines = nullptr; size_t lines_cap = 0;
     u64 *d_bases = nullptr, *d_nmask = nullptr; u32 *d_meta = nullptr; size_t rec_cap = 0;
+    u64 *d_q1 = nullptr; u32 *d_q2 = nullptr, *d_q3 = nullptr; u64 *d_qn = nullptr;   // K1 class queues (rec_cap entries each) and their fills
     // unique table
     void *d_slots = nullptr; u64 table_cap = 0;
     u64 max_unique = 0;
@@ -262,6 +264,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_todo[1], max_unique * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 1) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_carry, 16 * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_qn, 4 * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_round_stats, 2 * MIRGE_N_ROUNDS * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_lib_totals, (size_t)n_samples * MIRGE_N_TOTALS * sizeof(i64)));
     CK(cudaMemsetAsync(ctx->d_slots, 0, cap * esz, ctx->stream));
@@ -289,6 +292,7 @@ void mirge_destroy(mirge_ctx *ctx)
     for (int i = 0; i < MIRGE_N_LIBS; i++) free_lib(ctx->libs[i]);
     cudaFree(ctx->d_text); cudaFree(ctx->d_tile); cudaFree(ctx->d_scan); cudaFree(ctx->d_lines);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
+    cudaFree(ctx->d_q1); cudaFree(ctx->d_q2); cudaFree(ctx->d_q3); cudaFree(ctx->d_qn);
     cudaFree(ctx->d_slots); cudaFree(ctx->d_useq); cudaFree(ctx->d_unmask); cudaFree(ctx->d_ulen); cudaFree(ctx->d_counts);
     cudaFree(ctx->d_round_of); cudaFree(ctx->d_mm_of); cudaFree(ctx->d_ref_of); cudaFree(ctx->d_pos_of);
     cudaFree(ctx->d_ctr); cudaFree(ctx->d_len_hist); cudaFree(ctx->d_todo[0]); cudaFree(ctx->d_todo[1]);
@@ -452,19 +456,37 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
         if (nrec) {
             if (nrec > ctx->rec_cap) {
                 cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
+                cudaFree(ctx->d_q1); cudaFree(ctx->d_q2); cudaFree(ctx->d_q3);
                 ctx->d_bases = ctx->d_nmask = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
+                ctx->d_q1 = nullptr; ctx->d_q2 = ctx->d_q3 = nullptr;
                 const size_t cap = nrec + nrec / 8 + 64;
                 CK(cudaMalloc(&ctx->d_bases, cap * W * sizeof(u64)));
                 CK(cudaMalloc(&ctx->d_nmask, cap * (W / 2) * sizeof(u64)));
                 CK(cudaMalloc(&ctx->d_meta, cap * sizeof(u32)));
+                CK(cudaMalloc(&ctx->d_q1, cap * sizeof(u64)));
+                CK(cudaMalloc(&ctx->d_q2, cap * sizeof(u32)));
+                CK(cudaMalloc(&ctx->d_q3, cap * sizeof(u32)));
                 ctx->rec_cap = cap;
             }
             { ProfScope ps(ctx, KID_K0_PACK);
               k0_pack<W><<<grid_for(nrec, 256, 148 * 16), 256, 0, st>>>(d_text, ctx->d_lines, nrec, kp, ctx->d_bases, ctx->d_nmask,
                                                                        ctx->d_meta, (u32 *)(ctx->d_ctr + 1)); }
-            { ProfScope ps(ctx, KID_K1_TRIM);
-              k1_trim_collapse<W><<<grid_for(nrec, K1_THREADS, 148 * 16), K1_THREADS, 0, st>>>(
-                  ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->thr, ctx->pre, table_view<W>(ctx), kc, ctx->force_slow); }
+            { ProfScope ps(ctx, KID_K1_TRIM, 4);
+              K1Queues Q; Q.n = ctx->d_qn; Q.q1 = ctx->d_q1; Q.q2 = ctx->d_q2; Q.q3 = ctx->d_q3;
+              const TableView<W> T = table_view<W>(ctx);
+              CK(cudaMemsetAsync(ctx->d_qn, 0, 3 * sizeof(u64), st));
+              { ProfScope p1(ctx, KID_K1_CLASSIFY, 0);
+                k1_trim_collapse<W><<<grid_for(nrec, K1A_THREADS, 148 * 8), K1A_THREADS, 0, st>>>(
+                    ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->pre, T, kc, Q, ctx->force_slow); }
+              // the queue fills live on the device: fixed grids, grid-stride loops bounded by the fill
+              const int qgrid = grid_for(nrec, K1_THREADS, 148 * 8);
+              { ProfScope p1(ctx, KID_K1_SCAN, 0);
+                k1_scan_class1<W><<<qgrid, K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
+              { ProfScope p1(ctx, KID_K1_GENERAL, 0);
+                k1_general_search<W><<<qgrid, K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
+              { ProfScope p1(ctx, KID_K1_SLOW, 0);
+                k1_slow_search<W><<<qgrid, K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q,
+                                                                (ctx->force_slow & 2) ? 1 : 0); } }
         }
         // carry the pending line starts to the front for the next region
         const u32 q2 = (u32)(lines % 4);

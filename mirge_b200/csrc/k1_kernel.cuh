@@ -381,183 +381,245 @@ __device__ __forceinline__ int k1_trim_slow(const PSeq<W> &p, int n, const TrimP
     return best_rstart >= 0 ? best_rstart : n;
 }
 
+// Length filter + collapse for one converged warp: lanes with `on` hold a trimmed read of
+// n bases.  wh = this warp's private read-length histogram (shared memory).
 template <int W>
-__device__ __forceinline__ bool k1_finish(PSeq<W> &p, int n, const TrimParams &tp, const TableView<W> &T, int sample, u32 *sh_hist)
+__device__ __forceinline__ u32 k1_finish_warp(PSeq<W> &p, int n, bool on, int min_length, const TableView<W> &T, int sample, u32 *wh)
 {
-    if (n < tp.min_length) return false;
-    pseq_truncate<W>(p, n);
-    const u64 h = pseq_hash<W>(p, n);
-    const u32 id = table_upsert<W>(T, p, n, h);
-    if (id != 0xFFFFFFFFu) atomicAdd(&T.counts[(u64)id * T.S + sample], 1u);
-    atomicAdd(&sh_hist[n], 1u);
-    return true;
+    const bool keep = on && n >= min_length;
+    if (keep) pseq_truncate<W>(p, n);
+    table_add_warp<W>(T, p, n, keep, sample);
+    if (keep) atomicAdd(&wh[n], 1u);
+    return keep ? 1u : 0u;
 }
 
-// Reads queued by one warp for a later, fully converged pass.
-#define K1_Q1 64      // class 1: full-candidate scan
-#define K1_Q2 128     // class 2: windowed bit-vector search with candidate walks
-#define K1_Q3 128     // reads the windowed search could not settle
+// ---------------------------------------------------------------------------
+// K1 is a short pipeline of four kernels, each one homogeneous (small code, full
+// warps, its own occupancy):
+//   k1_trim_collapse  every read: prefilter; class 0 -> length filter + upsert;
+//                     class 1 / 2 -> appended to device queues
+//   k1_scan_class1    queue 1: full-candidate cost scan; clean -> upsert, else queue 2
+//   k1_general_search queue 2: windowed bit-vector search with candidate walks;
+//                     unsettled -> queue 3
+//   k1_slow_search    queue 3: all-column search (or the literal DP)
+// Queue appends are warp-aggregated (one atomic per warp and queue).
+// ---------------------------------------------------------------------------
+struct K1Queues {
+    u64 *n;           // [3] fills of q1, q2, q3
+    u64 *q1;          // record index | (rstart | limit << 8) << 32
+    u32 *q2;
+    u32 *q3;
+};
 
-// force_slow bits (parity tests): 1 = every read through the all-column search,
-// 2 = ... through the literal DP instead, 4 = prefilter off.
+struct K1Shared {
+    TrimParams tp;                                  // dynamic indexing by adapter: keep it out of local memory
+    signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
+    u32 peq8[MIRGE_MAX_ADAPTERS * 8];
+};
+
+// sh_hist holds one read-length histogram per warp ((32 W + 1) counters each): a warp
+// flushes its own when it is done, so no kernel needs a CTA barrier after its main loop.
+#define K1_HIST(W) (32 * (W) + 1)
+
 template <int W>
-__global__ void __launch_bounds__(K1_THREADS)
-k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-                 u64 n_records, int sample, TrimParams tp_param, K1Thr thr_param, K1Pre pre_param, TableView<W> T, K1Counters ctr,
-                 int force_slow)
+__device__ __forceinline__ void k1_setup(K1Shared &sh, u32 *sh_hist, const TrimParams &tp_param, const K1Thr &thr_param)
 {
-    __shared__ u64 ring[K1_RING * K1_THREADS];
-    __shared__ u32 ringh[K1_RING * K1_THREADS];
-    __shared__ u32 q1r[K1_THREADS / 32][K1_Q1];     // one set of queues per warp: no CTA-wide barrier in the main loop
-    __shared__ u16 q1i[K1_THREADS / 32][K1_Q1];     // rstart | limit << 8
-    __shared__ u32 q2[K1_THREADS / 32][K1_Q2];
-    __shared__ u32 q3[K1_THREADS / 32][K1_Q3];
-    __shared__ u32 sh_hist[32 * W + 1];
-    __shared__ TrimParams tp;                       // dynamic indexing by adapter: keep it out of local memory
-    __shared__ K1Pre pre;
-    __shared__ signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
-    __shared__ u32 peq8[MIRGE_MAX_ADAPTERS * 8];
-    for (int b = threadIdx.x; b <= 32 * W; b += K1_THREADS) sh_hist[b] = 0;
-    for (int b = threadIdx.x; b <= MIRGE_MAX_ADAPTER_LEN; b += K1_THREADS) thr[b] = thr_param.v[b];
-    for (int b = threadIdx.x; b < (int)(sizeof(TrimParams) / 4); b += K1_THREADS)
-        reinterpret_cast<u32 *>(&tp)[b] = reinterpret_cast<const u32 *>(&tp_param)[b];
-    for (int b = threadIdx.x; b < (int)(sizeof(K1Pre) / 4); b += K1_THREADS)
-        reinterpret_cast<u32 *>(&pre)[b] = reinterpret_cast<const u32 *>(&pre_param)[b];
+    for (int b = threadIdx.x; b < K1_HIST(W) * (int)(blockDim.x / 32); b += blockDim.x) sh_hist[b] = 0;
+    for (int b = threadIdx.x; b <= MIRGE_MAX_ADAPTER_LEN; b += blockDim.x) sh.thr[b] = thr_param.v[b];
+    for (int b = threadIdx.x; b < (int)(sizeof(TrimParams) / 4); b += blockDim.x)
+        reinterpret_cast<u32 *>(&sh.tp)[b] = reinterpret_cast<const u32 *>(&tp_param)[b];
     if (threadIdx.x < MIRGE_MAX_ADAPTERS * 8)
-        peq8[threadIdx.x] = (threadIdx.x & 4) ? 0u : (u32)tp_param.peq[threadIdx.x >> 3][threadIdx.x & 3];
+        sh.peq8[threadIdx.x] = (threadIdx.x & 4) ? 0u : (u32)tp_param.peq[threadIdx.x >> 3][threadIdx.x & 3];
     __syncthreads();
-    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned below = (1u << lane) - 1u;
-    const bool use_pre = pre.enabled && !(force_slow & 4);
-    const u64 aw0 = tp.aw[0][0];
-    const int thr_m0 = thr[tp.alen[0]];
-    u32 n1 = 0, n2 = 0, n3 = 0;                     // queue fills (warp-uniform)
-    u32 my_kept = 0, my_slow = 0, my_c1 = 0, my_c2 = 0;
-    u64 *my_ring = ring + threadIdx.x;
-    u32 *my_ringh = ringh + threadIdx.x;
-    for (u64 r0 = (u64)blockIdx.x * K1_THREADS; r0 < n_records; r0 += (u64)gridDim.x * K1_THREADS) {
-        const u64 r = r0 + threadIdx.x;
-        const bool live = r < n_records;
-        {
-            PSeq<W> p;
-            int n = 0;
-            if (live) k1_load_record<W>(bases, nmask, meta, r, p, n);
-            else {
-#pragma unroll
-                for (int w = 0; w < W; w++) p.s[w] = 0;
-#pragma unroll
-                for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
-            }
-            int nf = n, cls = 0, lim = 0;
-            if (tp.mode == 2) {
-                const int L = tp.uncond;
-                if (L > 0) { const int cut = L < n ? L : n; pseq_shift<W>(p, cut); nf = n - cut; }
-                else if (L < 0) { const int cut = (-L) < n ? (-L) : n; nf = n - cut; }
-            } else if (tp.mode == 1) {
-                if (force_slow & 3) cls = 3;
-                else if (use_pre) cls = k1_prefilter<W>(p, n, pre, aw0, nf, lim);
-                else cls = 2;
-            }
-            if (!live) cls = -1;
-            const unsigned b1 = __ballot_sync(0xffffffffu, cls == 1);
-            const unsigned b2 = __ballot_sync(0xffffffffu, cls == 2);
-            const unsigned b3 = __ballot_sync(0xffffffffu, cls == 3);
-            if (cls == 1) {
-                const u32 at = n1 + __popc(b1 & below);
-                q1r[wid][at] = (u32)r; q1i[wid][at] = (u16)(nf | (lim << 8));
-                my_c1++;
-            } else if (cls == 2) {
-                q2[wid][n2 + __popc(b2 & below)] = (u32)r;
-                my_c2++;
-            } else if (cls == 3) {
-                q3[wid][n3 + __popc(b3 & below)] = (u32)r;
-            }
-            n1 += __popc(b1); n2 += __popc(b2); n3 += __popc(b3);
-            if (cls == 0) my_kept += k1_finish<W>(p, nf, tp, T, sample, sh_hist) ? 1u : 0u;
-        }
-        __syncwarp();
-        // drain full warps of queued reads, and whatever is left after the last tile
-        const bool last_tile = r0 + (u64)gridDim.x * K1_THREADS >= n_records;
-        while (n1 >= 32 || (last_tile && n1 > 0)) {
-            const u32 take = n1 < 32 ? n1 : 32;
-            const bool on = lane < take;
-            PSeq<W> ps;
-            int ns = 0, lim = 0, rs = 0;
-            u32 rr = 0;
-            if (on) {
-                rr = q1r[wid][n1 - take + lane];
-                const u32 info = q1i[wid][n1 - take + lane];
-                rs = info & 0xFF; lim = info >> 8;
-                k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
-            } else {
-#pragma unroll
-                for (int w = 0; w < W; w++) ps.s[w] = 0;
-#pragma unroll
-                for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
-            }
-            const bool hit = k1_full_candidate_scan<W>(ps, lim, tp.alen[0], thr_m0, peq8);
-            n1 -= take;
-            __syncwarp();
-            const unsigned hb = __ballot_sync(0xffffffffu, on && hit);
-            if (on && hit) q2[wid][n2 + __popc(hb & below)] = rr;       // a full-length candidate: general search decides
-            n2 += __popc(hb);
-            if (on && !hit) my_kept += k1_finish<W>(ps, rs, tp, T, sample, sh_hist) ? 1u : 0u;
-            __syncwarp();
-        }
-        while (n2 >= 32 || (last_tile && n2 > 0)) {
-            const u32 take = n2 < 32 ? n2 : 32;
-            const bool on = lane < take;
-            PSeq<W> ps;
-            int ns = 0;
-            u32 rr = 0;
-            if (on) {
-                rr = q2[wid][n2 - take + lane];
-                k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
-            } else {
-#pragma unroll
-                for (int w = 0; w < W; w++) ps.s[w] = 0;
-#pragma unroll
-                for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
-            }
-            const int nfs = k1_trim_fast<W>(ps, ns, tp, thr, my_ring, my_ringh, peq8);       // warp-collective
-            n2 -= take;
-            __syncwarp();
-            const unsigned sb = __ballot_sync(0xffffffffu, on && nfs == K1_SLOW);
-            if (on && nfs == K1_SLOW) q3[wid][n3 + __popc(sb & below)] = rr;
-            n3 += __popc(sb);
-            if (on && nfs != K1_SLOW) my_kept += k1_finish<W>(ps, nfs, tp, T, sample, sh_hist) ? 1u : 0u;
-            __syncwarp();
-        }
-        while (n3 >= 32 || (last_tile && n3 > 0)) {
-            const u32 take = n3 < 32 ? n3 : 32;
-            if (lane < take) {
-                PSeq<W> ps;
-                int ns;
-                k1_load_record<W>(bases, nmask, meta, (u64)q3[wid][n3 - take + lane], ps, ns);
-                const int nfs = k1_trim_slow<W>(ps, ns, tp, thr, peq8, (force_slow & 2) != 0);
-                my_kept += k1_finish<W>(ps, nfs, tp, T, sample, sh_hist) ? 1u : 0u;
-                my_slow++;
-            }
-            n3 -= take;
-            __syncwarp();
-        }
-    }
+}
+
+template <int W>
+__device__ __forceinline__ void k1_teardown(u32 my_kept, u32 my_diag, u64 *diag, const u32 *sh_hist, const K1Counters &ctr, int S, int sample)
+{
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         my_kept += __shfl_down_sync(0xffffffffu, my_kept, d);
-        my_slow += __shfl_down_sync(0xffffffffu, my_slow, d);
-        my_c1 += __shfl_down_sync(0xffffffffu, my_c1, d);
-        my_c2 += __shfl_down_sync(0xffffffffu, my_c2, d);
+        my_diag += __shfl_down_sync(0xffffffffu, my_diag, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (my_kept) atomicAdd(&ctr.kept[sample], (u64)my_kept);
-        if (ctr.slow_reads) {
-            if (my_slow) atomicAdd(ctr.slow_reads, (u64)my_slow);
-            if (my_c1) atomicAdd(ctr.slow_reads + 1, (u64)my_c1);
-            if (my_c2) atomicAdd(ctr.slow_reads + 2, (u64)my_c2);
-        }
+        if (my_diag && diag) atomicAdd(diag, (u64)my_diag);
     }
+    __syncwarp();
+    const u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    for (int b = threadIdx.x & 31; b < K1_HIST(W); b += 32)
+        if (wh[b]) atomicAdd(&ctr.len_hist[(u64)b * S + sample], (u64)wh[b]);
+}
+
+// one atomic per warp: lanes with `push` set get consecutive slots of the queue
+__device__ __forceinline__ u64 k1_queue_slot(bool push, u64 *fill)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned b = __ballot_sync(0xffffffffu, push);
+    if (!b) return 0;
+    u64 base = 0;
+    if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(fill, (u64)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+    return base + __popc(b & ((1u << lane) - 1u));
+}
+
+// force_slow bits (parity tests): 1 = every read through the all-column search,
+// 2 = ... through the literal DP instead, 4 = prefilter off.
+#define K1A_THREADS 256
+template <int W>
+__global__ void __launch_bounds__(K1A_THREADS)
+k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
+                 u64 n_records, int sample, TrimParams tp_param, K1Pre pre_param, TableView<W> T, K1Counters ctr, K1Queues Q,
+                 int force_slow)
+{
+    __shared__ u32 sh_hist[K1_HIST(W) * (K1A_THREADS / 32)];
+    __shared__ K1Pre pre;
+    for (int b = threadIdx.x; b < K1_HIST(W) * (K1A_THREADS / 32); b += K1A_THREADS) sh_hist[b] = 0;
+    u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    for (int b = threadIdx.x; b < (int)(sizeof(K1Pre) / 4); b += K1A_THREADS)
+        reinterpret_cast<u32 *>(&pre)[b] = reinterpret_cast<const u32 *>(&pre_param)[b];
     __syncthreads();
-    for (int b = threadIdx.x; b <= 32 * W; b += K1_THREADS)
-        if (sh_hist[b]) atomicAdd(&ctr.len_hist[(u64)b * T.S + sample], (u64)sh_hist[b]);
+    const bool use_pre = pre.enabled && !(force_slow & 4);
+    const int mode = tp_param.mode, uncond = tp_param.uncond, min_length = tp_param.min_length;
+    const u64 aw0 = tp_param.aw[0][0];
+    u32 my_kept = 0;
+    for (u64 r0 = (u64)blockIdx.x * K1A_THREADS; r0 < n_records; r0 += (u64)gridDim.x * K1A_THREADS) {
+        const u64 r = r0 + threadIdx.x;
+        const bool live = r < n_records;
+        PSeq<W> p;
+        int n = 0;
+        if (live) k1_load_record<W>(bases, nmask, meta, r, p, n);
+        else {
+#pragma unroll
+            for (int w = 0; w < W; w++) p.s[w] = 0;
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
+        }
+        int nf = n, cls = 0, lim = 0;
+        if (mode == 2) {
+            if (uncond > 0) { const int cut = uncond < n ? uncond : n; pseq_shift<W>(p, cut); nf = n - cut; }
+            else if (uncond < 0) { const int cut = (-uncond) < n ? (-uncond) : n; nf = n - cut; }
+        } else if (mode == 1) {
+            if (force_slow & 3) cls = 3;
+            else if (use_pre) cls = k1_prefilter<W>(p, n, pre, aw0, nf, lim);
+            else cls = 2;
+        }
+        if (!live) cls = -1;
+        const u64 s1 = k1_queue_slot(cls == 1, Q.n + 0);
+        const u64 s2 = k1_queue_slot(cls == 2, Q.n + 1);
+        const u64 s3 = k1_queue_slot(cls == 3, Q.n + 2);
+        if (cls == 1) Q.q1[s1] = r | ((u64)(nf | (lim << 8)) << 32);
+        else if (cls == 2) Q.q2[s2] = (u32)r;
+        else if (cls == 3) Q.q3[s3] = (u32)r;
+        my_kept += k1_finish_warp<W>(p, nf, cls == 0, min_length, T, sample, wh);
+    }
+    k1_teardown<W>(my_kept, 0u, nullptr, sh_hist, ctr, T.S, sample);
+}
+
+template <int W>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_scan_class1(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
+               int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q)
+{
+    __shared__ u32 sh_hist[K1_HIST(W) * (K1_THREADS / 32)];
+    __shared__ u32 peq8[8];
+    for (int b = threadIdx.x; b < K1_HIST(W) * (K1_THREADS / 32); b += K1_THREADS) sh_hist[b] = 0;
+    u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    if (threadIdx.x < 8) peq8[threadIdx.x] = (threadIdx.x & 4) ? 0u : (u32)tp_param.peq[0][threadIdx.x & 3];
+    __syncthreads();
+    const u64 n1 = *Q.n;
+    const int m = tp_param.alen[0], thr_m = thr_param.v[m], min_length = tp_param.min_length;
+    u32 my_kept = 0, my_n = 0;
+    for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n1; i0 += (u64)gridDim.x * K1_THREADS) {
+        const u64 i = i0 + threadIdx.x;
+        const bool on = i < n1;
+        PSeq<W> ps;
+        int ns = 0, lim = 0, rs = 0;
+        u32 rr = 0;
+        if (on) {
+            const u64 e = Q.q1[i];
+            rr = (u32)e; rs = (int)((e >> 32) & 0xFF); lim = (int)(e >> 40);
+            k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
+            my_n++;
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; w++) ps.s[w] = 0;
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
+        }
+        const bool hit = k1_full_candidate_scan<W>(ps, lim, m, thr_m, peq8);
+        const u64 s2 = k1_queue_slot(on && hit, Q.n + 1);              // a full-length candidate: the general search decides
+        if (on && hit) Q.q2[s2] = rr;
+        my_kept += k1_finish_warp<W>(ps, rs, on && !hit, min_length, T, sample, wh);
+    }
+    k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 1 : nullptr, sh_hist, ctr, T.S, sample);
+}
+
+template <int W>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_general_search(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
+                  int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q)
+{
+    __shared__ u64 ring[K1_RING * K1_THREADS];
+    __shared__ u32 ringh[K1_RING * K1_THREADS];
+    __shared__ u32 sh_hist[K1_HIST(W) * (K1_THREADS / 32)];
+    __shared__ K1Shared sh;
+    k1_setup<W>(sh, sh_hist, tp_param, thr_param);
+    u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    const u64 n2 = Q.n[1];
+    u32 my_kept = 0, my_n = 0;
+    for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n2; i0 += (u64)gridDim.x * K1_THREADS) {
+        const u64 i = i0 + threadIdx.x;
+        const bool on = i < n2;
+        PSeq<W> ps;
+        int ns = 0;
+        u32 rr = 0;
+        if (on) {
+            rr = Q.q2[i];
+            k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
+            my_n++;
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; w++) ps.s[w] = 0;
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
+        }
+        const int nfs = k1_trim_fast<W>(ps, ns, sh.tp, sh.thr, ring + threadIdx.x, ringh + threadIdx.x, sh.peq8);   // warp-collective
+        const u64 s3 = k1_queue_slot(on && nfs == K1_SLOW, Q.n + 2);
+        if (on && nfs == K1_SLOW) Q.q3[s3] = rr;
+        my_kept += k1_finish_warp<W>(ps, nfs, on && nfs != K1_SLOW, sh.tp.min_length, T, sample, wh);
+    }
+    k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 2 : nullptr, sh_hist, ctr, T.S, sample);
+}
+
+template <int W>
+__global__ void __launch_bounds__(K1_THREADS)
+k1_slow_search(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
+               int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q, int literal)
+{
+    __shared__ u32 sh_hist[K1_HIST(W) * (K1_THREADS / 32)];
+    __shared__ K1Shared sh;
+    k1_setup<W>(sh, sh_hist, tp_param, thr_param);
+    u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    const u64 n3 = Q.n[2];
+    u32 my_kept = 0, my_n = 0;
+    for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n3; i0 += (u64)gridDim.x * K1_THREADS) {
+        const u64 i = i0 + threadIdx.x;
+        const bool on = i < n3;
+        PSeq<W> ps;
+        int ns = 0, nfs = 0;
+        if (on) {
+            k1_load_record<W>(bases, nmask, meta, (u64)Q.q3[i], ps, ns);
+            nfs = k1_trim_slow<W>(ps, ns, sh.tp, sh.thr, sh.peq8, literal != 0);
+            my_n++;
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; w++) ps.s[w] = 0;
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
+        }
+        __syncwarp();
+        my_kept += k1_finish_warp<W>(ps, nfs, on, sh.tp.min_length, T, sample, wh);
+    }
+    k1_teardown<W>(my_kept, my_n, ctr.slow_reads, sh_hist, ctr, T.S, sample);
 }

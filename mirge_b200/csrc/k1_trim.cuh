@@ -127,6 +127,93 @@ __device__ u32 table_upsert(const TableView<W> &T, const PSeq<W> &key, int len, 
     return 0xFFFFFFFFu;
 }
 
+// Warp-collective find-or-insert + count (the collapse of quantReads.py:9-16): every
+// lane of a converged warp calls it; lanes with `active` hold a key to be counted once.
+//   1. duplicates inside the warp are folded first (__match_any_sync on the 64-bit hash,
+//      keys compared with the group leader's): one lane per distinct key probes, and adds
+//      the group's size -- hot sequences cost one global atomic per warp, not per read;
+//   2. leaders probe until they hit, claim an empty slot, or meet a slot with their
+//      fingerprint that is still being published (they retry it after step 3);
+//   3. claiming lanes take their dense ids with one atomic, write their keys, execute ONE
+//      fence for the warp and publish their tags (the release side of the protocol above).
+template <int W>
+__device__ __forceinline__ void table_add_warp(const TableView<W> &T, const PSeq<W> &key, int len, bool active, int sample)
+{
+    const unsigned lane = threadIdx.x & 31, below = (1u << lane) - 1u;
+    const u64 h = active ? pseq_hash<W>(key, len) : 0ull;
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (!act) return;
+    const unsigned grp = __match_any_sync(0xffffffffu, h) & act;
+    const int leader = active ? (__ffs(grp) - 1) : (int)lane;
+    bool same = (__shfl_sync(0xffffffffu, len, leader) == len);
+#pragma unroll
+    for (int w = 0; w < W; w++) same = same && (__shfl_sync(0xffffffffu, key.s[w], leader) == key.s[w]);
+#pragma unroll
+    for (int w = 0; w < W / 2; w++) same = same && (__shfl_sync(0xffffffffu, key.nm[w], leader) == key.nm[w]);
+    const unsigned folded = __ballot_sync(0xffffffffu, active && same);
+    // a 64-bit hash collision between different keys of one warp: the odd lane inserts on its own
+    const bool lead = active && ((int)lane == leader || !same);
+    const u32 cnt = ((int)lane == leader) ? (u32)__popc(grp & folded) : 1u;
+    const u32 want = (((((u32)(h >> 41)) & 0x7FFFFFu) | 1u) << 9) | ((u32)len << 1);   // busy form (ready bit clear)
+    u64 slot = h & T.mask;
+    u64 probes = 0;
+    int state = lead ? 1 : 0;           // 1 probing, 2 claimed a slot, 0 done
+    u32 id = 0xFFFFFFFFu;
+    for (;;) {
+        if (state == 1) {
+            for (;;) {
+                if (probes > T.mask) { atomicOr(T.err, ERRF_FULL); state = 0; break; }
+                TEntry<W> *e = T.slots + slot;
+                u32 t = ld_acquire_u32(&e->tag);
+                if (t == 0) {
+                    const u32 old = atomicCAS(&e->tag, 0u, want);
+                    if (old == 0) { state = 2; break; }
+                    t = old;
+                }
+                if ((t | 1u) == (want | 1u)) {
+                    if (!(t & 1u)) break;                               // unpublished: look again after this warp's own publishes
+                    if (entry_key_equal<W>(e, key)) {
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(id) : "l"(&e->id) : "memory");
+                        state = 0;
+                        break;
+                    }
+                }
+                slot = (slot + 1) & T.mask;
+                probes++;
+            }
+        }
+        const unsigned cl = __ballot_sync(0xffffffffu, state == 2);
+        if (cl) {
+            const int first = __ffs(cl) - 1;
+            u64 base = 0;
+            if ((int)lane == first) base = atomicAdd(T.n_unique, (u64)__popc(cl));
+            base = __shfl_sync(0xffffffffu, base, first);
+            if (state == 2) {
+                const u64 nid = base + __popc(cl & below);
+                TEntry<W> *e = T.slots + slot;
+                if (nid < T.max_unique) id = (u32)nid; else atomicOr(T.err, ERRF_FULL);
+#pragma unroll
+                for (int w = 0; w < W; w++) e->s[w] = key.s[w];
+#pragma unroll
+                for (int w = 0; w < W / 2; w++) e->nm[w] = key.nm[w];
+                e->id = id;
+                __threadfence();
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(&e->tag), "r"(want | 1u) : "memory");   // publish
+                if (id != 0xFFFFFFFFu) {                                // dense copies: read by later kernels only
+#pragma unroll
+                    for (int w = 0; w < W; w++) T.useq[nid * W + w] = key.s[w];
+#pragma unroll
+                    for (int w = 0; w < W / 2; w++) T.unmask[nid * (W / 2) + w] = key.nm[w];
+                    T.ulen[nid] = (u8)len;
+                }
+                state = 0;
+            }
+        }
+        if (!__any_sync(0xffffffffu, state == 1)) break;
+    }
+    if (lead && id != 0xFFFFFFFFu) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt);
+}
+
 // ---------------------------------------------------------------------------
 // adapter matching
 // ---------------------------------------------------------------------------
