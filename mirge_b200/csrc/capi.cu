@@ -145,6 +145,17 @@ static int grid_for(u64 n, int threads, int max_blocks)
     return (int)b;
 }
 
+// One resident wave: grid = SM count x CTAs that fit per SM (the kernels use grid-stride loops).
+template <typename K>
+static int wave_grid(K kernel, int threads, u64 n_items)
+{
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return grid_for(n_items, threads, sms * per_sm);
+}
+
 template <int W>
 static TableView<W> table_view(mirge_ctx *c)
 {
@@ -260,8 +271,9 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_pos_of, max_unique * sizeof(int)));
     CK(cudaMalloc(&ctx->d_ctr, (5 + (size_t)n_samples) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_len_hist, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64)));
-    CK(cudaMalloc(&ctx->d_todo[0], max_unique * sizeof(u32)));
-    CK(cudaMalloc(&ctx->d_todo[1], max_unique * sizeof(u32)));
+    // to-do lists: every unique once, plus the partly used chunk of every appending warp
+    CK(cudaMalloc(&ctx->d_todo[0], (max_unique + (size_t)WARPQ_CHUNK * 148 * 64) * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo[1], (max_unique + (size_t)WARPQ_CHUNK * 148 * 64) * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 1) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_carry, 16 * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_qn, 4 * sizeof(u64)));
@@ -463,9 +475,11 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
                 CK(cudaMalloc(&ctx->d_bases, cap * W * sizeof(u64)));
                 CK(cudaMalloc(&ctx->d_nmask, cap * (W / 2) * sizeof(u64)));
                 CK(cudaMalloc(&ctx->d_meta, cap * sizeof(u32)));
-                CK(cudaMalloc(&ctx->d_q1, cap * sizeof(u64)));
-                CK(cudaMalloc(&ctx->d_q2, cap * sizeof(u32)));
-                CK(cudaMalloc(&ctx->d_q3, cap * sizeof(u32)));
+                // queues: every record once, plus the partly used chunk of every warp that appends
+                const size_t qcap = cap + (size_t)WARPQ_CHUNK * 3 * 148 * 64;
+                CK(cudaMalloc(&ctx->d_q1, qcap * sizeof(u64)));
+                CK(cudaMalloc(&ctx->d_q2, qcap * sizeof(u32)));
+                CK(cudaMalloc(&ctx->d_q3, qcap * sizeof(u32)));
                 ctx->rec_cap = cap;
             }
             { ProfScope ps(ctx, KID_K0_PACK);
@@ -476,16 +490,15 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
               const TableView<W> T = table_view<W>(ctx);
               CK(cudaMemsetAsync(ctx->d_qn, 0, 3 * sizeof(u64), st));
               { ProfScope p1(ctx, KID_K1_CLASSIFY, 0);
-                k1_trim_collapse<W><<<grid_for(nrec, K1A_THREADS, 148 * 8), K1A_THREADS, 0, st>>>(
+                k1_trim_collapse<W><<<wave_grid(k1_trim_collapse<W>, K1A_THREADS, nrec), K1A_THREADS, 0, st>>>(
                     ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->pre, T, kc, Q, ctx->force_slow); }
               // the queue fills live on the device: fixed grids, grid-stride loops bounded by the fill
-              const int qgrid = grid_for(nrec, K1_THREADS, 148 * 8);
               { ProfScope p1(ctx, KID_K1_SCAN, 0);
-                k1_scan_class1<W><<<qgrid, K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
+                k1_scan_class1<W><<<wave_grid(k1_scan_class1<W>, K1_THREADS, nrec), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
               { ProfScope p1(ctx, KID_K1_GENERAL, 0);
-                k1_general_search<W><<<qgrid, K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
+                k1_general_search<W><<<wave_grid(k1_general_search<W>, K1_THREADS, nrec), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
               { ProfScope p1(ctx, KID_K1_SLOW, 0);
-                k1_slow_search<W><<<qgrid, K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q,
+                k1_slow_search<W><<<wave_grid(k1_slow_search<W>, K1_THREADS, nrec), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q,
                                                                 (ctx->force_slow & 2) ? 1 : 0); } }
         }
         // carry the pending line starts to the front for the next region
@@ -660,7 +673,7 @@ static int annotate_impl(mirge_ctx *ctx)
         RoundParams R;
         memset(&R, 0, sizeof R);
         R.round = r; R.len_filter = rs.len_filter; R.mode = rs.mode; R.param = rs.param; R.trim5 = rs.trim5; R.trim3 = rs.trim3;
-        R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs;
+        R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs; R.chunked = (ctx->force_slow & 0x1000) ? 1 : 0;   // per-tile appends measured faster for the heavy rounds
         for (int t = 0; t < l.ntabs; t++) { R.tabs[t].k = l.tab_k[t]; R.tabs[t].bucket_off = l.tab_off[t]; R.tabs[t].pos = l.tab_pos[t]; }
         const u32 *todo_in = r == 0 ? nullptr : ctx->d_todo[(r - 1) & 1];
         const u64 *n_in = r == 0 ? ctx->d_ctr : ctx->d_todo_n + r;

@@ -182,6 +182,43 @@ __device__ __forceinline__ u32 mask_window32(const u64 *a, int so)
 }
 
 // ---------------------------------------------------------------------------
+// Device work queues (K1 class queues, K2 to-do lists).  A warp reserves WARPQ_CHUNK consecutive entries with one atomic and hands
+// them out to its lanes; what it does not use is padded with WARPQ_NONE (consumers skip it).
+// Atomics on the three fill counters -- one L2 sector -- would otherwise serialise the
+// whole kernel (same-address atomics retire at about one per nanosecond).
+#define WARPQ_CHUNK 128
+#define WARPQ_NONE 0xFFFFFFFFu
+struct WarpQ { u64 pos; u32 left; };       // warp-uniform
+
+template <typename E>
+__device__ __forceinline__ u64 warpq_slot(bool push, u64 *fill, E *q, WarpQ &wq)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned b = __ballot_sync(0xffffffffu, push);
+    const u32 c = __popc(b);
+    if (!c) return 0;
+    const u32 rank = __popc(b & ((1u << lane) - 1u));
+    if (c <= wq.left) {
+        const u64 slot = wq.pos + rank;
+        wq.pos += c; wq.left -= c;
+        return slot;
+    }
+    // the old chunk takes the first `left` entries, a fresh chunk the rest
+    u64 nb = 0;
+    if (lane == 0) nb = atomicAdd(fill, (u64)WARPQ_CHUNK);
+    nb = __shfl_sync(0xffffffffu, nb, 0);
+    const u32 spill = c - wq.left;
+    const u64 slot = rank < wq.left ? wq.pos + rank : nb + (rank - wq.left);
+    wq.pos = nb + spill; wq.left = WARPQ_CHUNK - spill;
+    return slot;
+}
+template <typename E>
+__device__ __forceinline__ void warpq_close(E *q, const WarpQ &wq)
+{
+    for (u32 x = threadIdx.x & 31; x < wq.left; x += 32) q[wq.pos + x] = (E)~(E)0;
+}
+
+// ---------------------------------------------------------------------------
 // block-wide exclusive scan of one u32 per thread (blockDim.x multiple of 32, <= 1024)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ u32 warp_incl_scan(u32 v)

@@ -388,7 +388,7 @@ __device__ __forceinline__ u32 k1_finish_warp(PSeq<W> &p, int n, bool on, int mi
 {
     const bool keep = on && n >= min_length;
     if (keep) pseq_truncate<W>(p, n);
-    table_add_warp<W>(T, p, n, keep, sample);
+    table_add_warp<W>(T, p, n, keep, sample, keep ? pseq_hash<W>(p, n) : 0ull);
     if (keep) atomicAdd(&wh[n], 1u);
     return keep ? 1u : 0u;
 }
@@ -417,14 +417,14 @@ struct K1Shared {
     u32 peq8[MIRGE_MAX_ADAPTERS * 8];
 };
 
-// sh_hist holds one read-length histogram per warp ((32 W + 1) counters each): a warp
-// flushes its own when it is done, so no kernel needs a CTA barrier after its main loop.
+// sh_hist: the CTA's read-length histogram, flushed once per CTA (global atomics on the
+// few histogram sectors are same-address traffic: keep them rare).
 #define K1_HIST(W) (32 * (W) + 1)
 
 template <int W>
 __device__ __forceinline__ void k1_setup(K1Shared &sh, u32 *sh_hist, const TrimParams &tp_param, const K1Thr &thr_param)
 {
-    for (int b = threadIdx.x; b < K1_HIST(W) * (int)(blockDim.x / 32); b += blockDim.x) sh_hist[b] = 0;
+    for (int b = threadIdx.x; b < K1_HIST(W); b += blockDim.x) sh_hist[b] = 0;
     for (int b = threadIdx.x; b <= MIRGE_MAX_ADAPTER_LEN; b += blockDim.x) sh.thr[b] = thr_param.v[b];
     for (int b = threadIdx.x; b < (int)(sizeof(TrimParams) / 4); b += blockDim.x)
         reinterpret_cast<u32 *>(&sh.tp)[b] = reinterpret_cast<const u32 *>(&tp_param)[b];
@@ -445,22 +445,9 @@ __device__ __forceinline__ void k1_teardown(u32 my_kept, u32 my_diag, u64 *diag,
         if (my_kept) atomicAdd(&ctr.kept[sample], (u64)my_kept);
         if (my_diag && diag) atomicAdd(diag, (u64)my_diag);
     }
-    __syncwarp();
-    const u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
-    for (int b = threadIdx.x & 31; b < K1_HIST(W); b += 32)
-        if (wh[b]) atomicAdd(&ctr.len_hist[(u64)b * S + sample], (u64)wh[b]);
-}
-
-// one atomic per warp: lanes with `push` set get consecutive slots of the queue
-__device__ __forceinline__ u64 k1_queue_slot(bool push, u64 *fill)
-{
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned b = __ballot_sync(0xffffffffu, push);
-    if (!b) return 0;
-    u64 base = 0;
-    if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(fill, (u64)__popc(b));
-    base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
-    return base + __popc(b & ((1u << lane) - 1u));
+    __syncthreads();
+    for (int b = threadIdx.x; b < K1_HIST(W); b += blockDim.x)
+        if (sh_hist[b]) atomicAdd(&ctr.len_hist[(u64)b * S + sample], (u64)sh_hist[b]);
 }
 
 // force_slow bits (parity tests): 1 = every read through the all-column search,
@@ -472,10 +459,13 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
                  u64 n_records, int sample, TrimParams tp_param, K1Pre pre_param, TableView<W> T, K1Counters ctr, K1Queues Q,
                  int force_slow)
 {
-    __shared__ u32 sh_hist[K1_HIST(W) * (K1A_THREADS / 32)];
+    __shared__ u32 sh_hist[K1_HIST(W)];
+    __shared__ u32 sh_cid[K1_CC * (K1A_THREADS / 32)], sh_ccnt[K1_CC * (K1A_THREADS / 32)];
     __shared__ K1Pre pre;
-    for (int b = threadIdx.x; b < K1_HIST(W) * (K1A_THREADS / 32); b += K1A_THREADS) sh_hist[b] = 0;
-    u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    for (int b = threadIdx.x; b < K1_HIST(W); b += K1A_THREADS) sh_hist[b] = 0;
+    for (int b = threadIdx.x; b < K1_CC * (K1A_THREADS / 32); b += K1A_THREADS) { sh_cid[b] = 0xFFFFFFFFu; sh_ccnt[b] = 0; }
+    u32 *wh = sh_hist;
+    u32 *cid = sh_cid + K1_CC * (threadIdx.x / 32), *ccnt = sh_ccnt + K1_CC * (threadIdx.x / 32);
     for (int b = threadIdx.x; b < (int)(sizeof(K1Pre) / 4); b += K1A_THREADS)
         reinterpret_cast<u32 *>(&pre)[b] = reinterpret_cast<const u32 *>(&pre_param)[b];
     __syncthreads();
@@ -483,6 +473,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
     const int mode = tp_param.mode, uncond = tp_param.uncond, min_length = tp_param.min_length;
     const u64 aw0 = tp_param.aw[0][0];
     u32 my_kept = 0;
+    WarpQ wq1 = {0, 0}, wq2 = {0, 0}, wq3 = {0, 0};
     for (u64 r0 = (u64)blockIdx.x * K1A_THREADS; r0 < n_records; r0 += (u64)gridDim.x * K1A_THREADS) {
         const u64 r = r0 + threadIdx.x;
         const bool live = r < n_records;
@@ -505,14 +496,24 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
             else cls = 2;
         }
         if (!live) cls = -1;
-        const u64 s1 = k1_queue_slot(cls == 1, Q.n + 0);
-        const u64 s2 = k1_queue_slot(cls == 2, Q.n + 1);
-        const u64 s3 = k1_queue_slot(cls == 3, Q.n + 2);
+        const u64 s1 = warpq_slot(cls == 1, Q.n + 0, Q.q1, wq1);
+        const u64 s2 = warpq_slot(cls == 2, Q.n + 1, Q.q2, wq2);
+        const u64 s3 = warpq_slot(cls == 3, Q.n + 2, Q.q3, wq3);
         if (cls == 1) Q.q1[s1] = r | ((u64)(nf | (lim << 8)) << 32);
         else if (cls == 2) Q.q2[s2] = (u32)r;
         else if (cls == 3) Q.q3[s3] = (u32)r;
-        my_kept += k1_finish_warp<W>(p, nf, cls == 0, min_length, T, sample, wh);
+        const bool keep = cls == 0 && nf >= min_length;
+        if (force_slow & 0x200) { my_kept += keep; continue; }             // diagnostic: classification only
+        if (keep) pseq_truncate<W>(p, nf);
+        bool lead; u32 id, cnt;
+        table_find_warp<W>(T, p, nf, keep, keep ? pseq_hash<W>(p, nf) : 0ull, lead, id, cnt);
+        if (force_slow & 0x100) { }                                        // diagnostic: no count updates
+        else if (force_slow & 0x800) { if (lead) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt); }   // count cache off
+        else count_cached<W>(cid, ccnt, T, sample, lead, id, cnt);
+        if (keep) { atomicAdd(&wh[nf], 1u); my_kept++; }
     }
+    count_cache_flush<W>(cid, ccnt, T, sample);
+    warpq_close(Q.q1, wq1); warpq_close(Q.q2, wq2); warpq_close(Q.q3, wq3);
     k1_teardown<W>(my_kept, 0u, nullptr, sh_hist, ctr, T.S, sample);
 }
 
@@ -521,23 +522,24 @@ __global__ void __launch_bounds__(K1_THREADS)
 k1_scan_class1(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
                int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q)
 {
-    __shared__ u32 sh_hist[K1_HIST(W) * (K1_THREADS / 32)];
+    __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ u32 peq8[8];
-    for (int b = threadIdx.x; b < K1_HIST(W) * (K1_THREADS / 32); b += K1_THREADS) sh_hist[b] = 0;
-    u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    for (int b = threadIdx.x; b < K1_HIST(W); b += K1_THREADS) sh_hist[b] = 0;
+    u32 *wh = sh_hist;
     if (threadIdx.x < 8) peq8[threadIdx.x] = (threadIdx.x & 4) ? 0u : (u32)tp_param.peq[0][threadIdx.x & 3];
     __syncthreads();
     const u64 n1 = *Q.n;
     const int m = tp_param.alen[0], thr_m = thr_param.v[m], min_length = tp_param.min_length;
     u32 my_kept = 0, my_n = 0;
+    WarpQ wq2 = {0, 0};
     for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n1; i0 += (u64)gridDim.x * K1_THREADS) {
         const u64 i = i0 + threadIdx.x;
-        const bool on = i < n1;
+        const u64 e = i < n1 ? Q.q1[i] : ~0ull;
+        const bool on = e != ~0ull;
         PSeq<W> ps;
         int ns = 0, lim = 0, rs = 0;
         u32 rr = 0;
         if (on) {
-            const u64 e = Q.q1[i];
             rr = (u32)e; rs = (int)((e >> 32) & 0xFF); lim = (int)(e >> 40);
             k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
             my_n++;
@@ -548,10 +550,11 @@ k1_scan_class1(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, con
             for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
         }
         const bool hit = k1_full_candidate_scan<W>(ps, lim, m, thr_m, peq8);
-        const u64 s2 = k1_queue_slot(on && hit, Q.n + 1);              // a full-length candidate: the general search decides
+        const u64 s2 = warpq_slot(on && hit, Q.n + 1, Q.q2, wq2);   // a full-length candidate: the general search decides
         if (on && hit) Q.q2[s2] = rr;
         my_kept += k1_finish_warp<W>(ps, rs, on && !hit, min_length, T, sample, wh);
     }
+    warpq_close(Q.q2, wq2);
     k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 1 : nullptr, sh_hist, ctr, T.S, sample);
 }
 
@@ -562,20 +565,20 @@ k1_general_search(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, 
 {
     __shared__ u64 ring[K1_RING * K1_THREADS];
     __shared__ u32 ringh[K1_RING * K1_THREADS];
-    __shared__ u32 sh_hist[K1_HIST(W) * (K1_THREADS / 32)];
+    __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ K1Shared sh;
     k1_setup<W>(sh, sh_hist, tp_param, thr_param);
-    u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    u32 *wh = sh_hist;
     const u64 n2 = Q.n[1];
     u32 my_kept = 0, my_n = 0;
+    WarpQ wq3 = {0, 0};
     for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n2; i0 += (u64)gridDim.x * K1_THREADS) {
         const u64 i = i0 + threadIdx.x;
-        const bool on = i < n2;
+        const u32 rr = i < n2 ? Q.q2[i] : WARPQ_NONE;
+        const bool on = rr != WARPQ_NONE;
         PSeq<W> ps;
         int ns = 0;
-        u32 rr = 0;
         if (on) {
-            rr = Q.q2[i];
             k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
             my_n++;
         } else {
@@ -585,10 +588,11 @@ k1_general_search(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, 
             for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
         }
         const int nfs = k1_trim_fast<W>(ps, ns, sh.tp, sh.thr, ring + threadIdx.x, ringh + threadIdx.x, sh.peq8);   // warp-collective
-        const u64 s3 = k1_queue_slot(on && nfs == K1_SLOW, Q.n + 2);
+        const u64 s3 = warpq_slot(on && nfs == K1_SLOW, Q.n + 2, Q.q3, wq3);
         if (on && nfs == K1_SLOW) Q.q3[s3] = rr;
         my_kept += k1_finish_warp<W>(ps, nfs, on && nfs != K1_SLOW, sh.tp.min_length, T, sample, wh);
     }
+    warpq_close(Q.q3, wq3);
     k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 2 : nullptr, sh_hist, ctr, T.S, sample);
 }
 
@@ -597,19 +601,20 @@ __global__ void __launch_bounds__(K1_THREADS)
 k1_slow_search(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
                int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q, int literal)
 {
-    __shared__ u32 sh_hist[K1_HIST(W) * (K1_THREADS / 32)];
+    __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ K1Shared sh;
     k1_setup<W>(sh, sh_hist, tp_param, thr_param);
-    u32 *wh = sh_hist + K1_HIST(W) * (threadIdx.x / 32);
+    u32 *wh = sh_hist;
     const u64 n3 = Q.n[2];
     u32 my_kept = 0, my_n = 0;
     for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n3; i0 += (u64)gridDim.x * K1_THREADS) {
         const u64 i = i0 + threadIdx.x;
-        const bool on = i < n3;
+        const u32 rr = i < n3 ? Q.q3[i] : WARPQ_NONE;
+        const bool on = rr != WARPQ_NONE;
         PSeq<W> ps;
         int ns = 0, nfs = 0;
         if (on) {
-            k1_load_record<W>(bases, nmask, meta, (u64)Q.q3[i], ps, ns);
+            k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
             nfs = k1_trim_slow<W>(ps, ns, sh.tp, sh.thr, sh.peq8, literal != 0);
             my_n++;
         } else {

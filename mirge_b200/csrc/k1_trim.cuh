@@ -136,11 +136,20 @@ __device__ u32 table_upsert(const TableView<W> &T, const PSeq<W> &key, int len, 
 //      fingerprint that is still being published (they retry it after step 3);
 //   3. claiming lanes take their dense ids with one atomic, write their keys, execute ONE
 //      fence for the warp and publish their tags (the release side of the protocol above).
+// Pull the home slot of hash h into L2 ahead of the probe.
 template <int W>
-__device__ __forceinline__ void table_add_warp(const TableView<W> &T, const PSeq<W> &key, int len, bool active, int sample)
+__device__ __forceinline__ void table_prefetch(const TableView<W> &T, u64 h)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(T.slots + (h & T.mask)));
+}
+
+template <int W>
+__device__ __forceinline__ void table_find_warp(const TableView<W> &T, const PSeq<W> &key, int len, bool active, u64 h,
+                                                bool &lead_out, u32 &id_out, u32 &cnt_out)
 {
     const unsigned lane = threadIdx.x & 31, below = (1u << lane) - 1u;
-    const u64 h = active ? pseq_hash<W>(key, len) : 0ull;
+    if (!active) h = 0ull;
+    lead_out = false; id_out = 0xFFFFFFFFu; cnt_out = 0;
     const unsigned act = __ballot_sync(0xffffffffu, active);
     if (!act) return;
     const unsigned grp = __match_any_sync(0xffffffffu, h) & act;
@@ -211,7 +220,50 @@ __device__ __forceinline__ void table_add_warp(const TableView<W> &T, const PSeq
         }
         if (!__any_sync(0xffffffffu, state == 1)) break;
     }
-    if (lead && id != 0xFFFFFFFFu) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt);
+    lead_out = lead && id != 0xFFFFFFFFu; id_out = id; cnt_out = cnt;
+}
+
+template <int W>
+__device__ __forceinline__ void table_add_warp(const TableView<W> &T, const PSeq<W> &key, int len, bool active, int sample, u64 h)
+{
+    bool lead; u32 id, cnt;
+    table_find_warp<W>(T, key, len, active, h, lead, id, cnt);
+    if (lead) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt);
+}
+
+// Per-warp write-back cache of pending count increments (shared memory, direct mapped
+// by id): the few very abundant sequences of a small-RNA sample would otherwise send
+// millions of atomics to the same few addresses.  cid/ccnt: this warp's K1_CC entries.
+#define K1_CC 128
+template <int W>
+__device__ __forceinline__ void count_cached(u32 *cid, u32 *ccnt, const TableView<W> &T, int sample, bool lead, u32 id, u32 cnt)
+{
+    const unsigned lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, lead);
+    const u32 slot = id & (K1_CC - 1);
+    while (todo) {
+        const bool pend = (todo >> lane) & 1u;
+        const unsigned grp = __match_any_sync(0xffffffffu, pend ? slot : (u32)(K1_CC + lane));
+        const bool act = pend && ((unsigned)(__ffs(grp) - 1) == lane);       // one lane per cache entry and round
+        if (act) {
+            const u32 c = cid[slot];
+            if (c == id) ccnt[slot] += cnt;
+            else {
+                const u32 oc = ccnt[slot];
+                if (oc) atomicAdd(&T.counts[(u64)c * T.S + sample], oc);
+                cid[slot] = id; ccnt[slot] = cnt;
+            }
+        }
+        __syncwarp();
+        todo &= ~__ballot_sync(0xffffffffu, act);
+    }
+}
+template <int W>
+__device__ __forceinline__ void count_cache_flush(u32 *cid, u32 *ccnt, const TableView<W> &T, int sample)
+{
+    __syncwarp();
+    for (int b = threadIdx.x & 31; b < K1_CC; b += 32)
+        if (ccnt[b]) atomicAdd(&T.counts[(u64)cid[b] * T.S + sample], ccnt[b]);
 }
 
 // ---------------------------------------------------------------------------

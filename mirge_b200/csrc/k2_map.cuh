@@ -40,6 +40,7 @@ struct RoundParams {
     int highest;        // keep the highest (ref, pos) of the best stratum
     int polyT;          // pre-tRNA round: strip trailing T{3,}, remainder >= 11 (:664-686)
     int ntabs;
+    int chunked;        // to-do appends: 1 = chunk reservation per warp (lists hold padding), 0 = one atomic per warp and tile
     KmerTab tabs[K2_MAX_TABS];   // ascending k
 };
 
@@ -197,17 +198,18 @@ k2_round(K2Arrays A, const u32 *__restrict__ todo_in, const u64 *__restrict__ n_
     const unsigned lane = threadIdx.x & 31;
     u32 my_proc = 0, my_aln = 0;
     const int nseeds = R.param + 1;
+    WarpQ wq = {0, 0};
     for (u64 base = (u64)blockIdx.x * blockDim.x; base < n_in; base += (u64)gridDim.x * blockDim.x) {
         const u64 i = base + threadIdx.x;
-        const bool active = i < n_in;
-        u32 id = 0;
+        u32 id = WARPQ_NONE;
+        if (i < n_in) id = todo_in ? todo_in[i] : (u32)i;
+        const bool active = id != WARPQ_NONE;                // lists hold padding (common.cuh:warpq_slot)
         bool pass = false;
         Query<W> q;
         q.n = 0;
 #pragma unroll
         for (int w = 0; w < W; w++) { q.s[w] = 0; q.n2[w] = 0; q.len2[w] = 0; }
         if (active) {
-            id = todo_in ? todo_in[i] : (u32)i;
             const int len = A.ulen[id];
             pass = L.seq != nullptr;
             if (R.len_filter < 0 && !(len < -R.len_filter)) pass = false;
@@ -308,15 +310,21 @@ k2_round(K2Arrays A, const u32 *__restrict__ todo_in, const u64 *__restrict__ n_
             my_aln++;
         }
         const bool push = active && !hit;
-        const unsigned bal = __ballot_sync(0xffffffffu, push);
-        if (bal) {
-            const int leader = __ffs(bal) - 1;
-            u64 b0 = 0;
-            if ((int)lane == leader) b0 = atomicAdd(n_out_ptr, (u64)__popc(bal));
-            b0 = __shfl_sync(0xffffffffu, b0, leader);
-            if (push) todo_out[b0 + __popc(bal & ((1u << lane) - 1u))] = id;
+        if (R.chunked) {
+            const u64 at = warpq_slot(push, n_out_ptr, todo_out, wq);
+            if (push) todo_out[at] = id;
+        } else {
+            const unsigned bal = __ballot_sync(0xffffffffu, push);
+            if (bal) {
+                const int leader = __ffs(bal) - 1;
+                u64 b0 = 0;
+                if ((int)lane == leader) b0 = atomicAdd(n_out_ptr, (u64)__popc(bal));
+                b0 = __shfl_sync(0xffffffffu, b0, leader);
+                if (push) todo_out[b0 + __popc(bal & ((1u << lane) - 1u))] = id;
+            }
         }
     }
+    warpq_close(todo_out, wq);
     // per-warp statistics
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
