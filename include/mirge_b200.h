@@ -162,6 +162,14 @@ int mirge_debug(mirge_ctx *ctx, int force_slow, uint64_t *slow_reads);
  * all-column search, reads the prefilter sent to the full-candidate scan
  * (class 1), reads it sent to the general search (class 2).  Synchronises. */
 int mirge_trim_classes(mirge_ctx *ctx, uint64_t *out3);
+/* The tables behind the trim kernel's exact-match prefilter for ONE 3' adapter
+ * (mirge_b200/csrc/k1_prefilter.cuh): returns 1 and fills m, icap, safe_p,
+ * safe_len[49] (index = insert length I, bit l) and fullreach[32] (index = l)
+ * when the prefilter applies (8 <= adapter length <= 32), 0 when every read takes
+ * the general search, negative on a bad argument.  Host-side, pure; lets the CPU
+ * tests check the tables against the oracle without a GPU. */
+int mirge_prefilter_tables(const char *adapter, double error_rate, int min_overlap, int *m, int *icap,
+                           uint32_t *safe_p, uint32_t *safe_len, uint8_t *fullreach);
 /* Number of kernels this library has launched on the context so far. */
 uint64_t mirge_launch_count(const mirge_ctx *ctx);
 

@@ -33,6 +33,7 @@ _SIGS = {
     'mirge_launch_count': (u64, [ctx_p]),
     'mirge_debug': (C.c_int, [ctx_p, C.c_int, vp]),
     'mirge_trim_classes': (C.c_int, [ctx_p, vp]),
+    'mirge_prefilter_tables': (C.c_int, [C.c_char_p, C.c_double, C.c_int, vp, vp, vp, vp, vp]),
     'mirge_set_adapter': (C.c_int, [ctx_p, C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_int]),
     'mirge_detect_phred': (C.c_int, [vp, u64]),
     'mirge_feed_fastq': (C.c_int, [ctx_p, C.c_int, vp, u64, C.c_int]),

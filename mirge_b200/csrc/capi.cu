@@ -930,6 +930,37 @@ int mirge_import_records_device(mirge_ctx *ctx, const void *dev_buf, uint64_t n_
     return MIRGE_OK;
 }
 
+int mirge_prefilter_tables(const char *adapter, double error_rate, int min_overlap, int *m_out, int *icap_out,
+                           uint32_t *safe_p, uint32_t *safe_len, uint8_t *fullreach)
+{
+    if (!adapter) return MIRGE_E_ARG;
+    TrimParams tp;
+    memset(&tp, 0, sizeof tp);
+    tp.mode = 1; tp.n_adapters = 1; tp.error_rate = error_rate; tp.min_overlap = min_overlap;
+    const size_t n = strlen(adapter);
+    if (n == 0 || n > MIRGE_MAX_ADAPTER_LEN) return MIRGE_E_ARG;
+    tp.alen[0] = (int)n;
+    for (size_t i = 0; i < n; i++) {
+        const int c = base_code((unsigned char)adapter[i]);
+        if (c > 3) return MIRGE_E_ARG;
+        tp.aw[0][i >> 5] |= (u64)c << ((i & 31) * 2);
+    }
+    K1Thr thr;
+    for (int i = 0; i <= MIRGE_MAX_ADAPTER_LEN; i++) {
+        int c = -1;
+        if (i >= min_overlap) { c = 0; while ((double)(c + 1) <= (double)i * error_rate) c++; }
+        thr.v[i] = (signed char)c;
+    }
+    K1Pre pre;
+    k1pre_build(tp, thr, pre);
+    if (m_out) *m_out = pre.m;
+    if (icap_out) *icap_out = pre.icap;
+    if (safe_p) *safe_p = pre.safe_p;
+    if (safe_len) memcpy(safe_len, pre.safe_len, sizeof pre.safe_len);
+    if (fullreach) memcpy(fullreach, pre.fullreach, sizeof pre.fullreach);
+    return pre.enabled;
+}
+
 uint64_t mirge_hash_sequence(const char *seq, int len)
 {
     u64 s[4] = {0, 0, 0, 0}, nm[2] = {0, 0};
