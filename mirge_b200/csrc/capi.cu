@@ -67,7 +67,7 @@ struct mirge_ctx {
     u32 *d_scan = nullptr; size_t scan_cap = 0;
     u32 *d_lines = nullptr; size_t lines_cap = 0;
     u64 *d_bases = nullptr, *d_nmask = nullptr; u32 *d_meta = nullptr; size_t rec_cap = 0;
-    u64 *d_q1 = nullptr; u32 *d_q2 = nullptr, *d_q3 = nullptr; u64 *d_qn = nullptr;   // K1 class queues (rec_cap entries each) and their fills
+    u64 *d_q1 = nullptr; u32 *d_q2 = nullptr, *d_q3 = nullptr; u64 *d_qn = nullptr, *d_part = nullptr;   // K1 class queues (rec_cap entries each), their fills; exchange partition counters
     // unique table
     void *d_slots = nullptr; u64 table_cap = 0;
     u64 max_unique = 0;
@@ -304,7 +304,7 @@ void mirge_destroy(mirge_ctx *ctx)
     for (int i = 0; i < MIRGE_N_LIBS; i++) free_lib(ctx->libs[i]);
     cudaFree(ctx->d_text); cudaFree(ctx->d_tile); cudaFree(ctx->d_scan); cudaFree(ctx->d_lines);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
-    cudaFree(ctx->d_q1); cudaFree(ctx->d_q2); cudaFree(ctx->d_q3); cudaFree(ctx->d_qn);
+    cudaFree(ctx->d_q1); cudaFree(ctx->d_q2); cudaFree(ctx->d_q3); cudaFree(ctx->d_qn); cudaFree(ctx->d_part);
     cudaFree(ctx->d_slots); cudaFree(ctx->d_useq); cudaFree(ctx->d_unmask); cudaFree(ctx->d_ulen); cudaFree(ctx->d_counts);
     cudaFree(ctx->d_round_of); cudaFree(ctx->d_mm_of); cudaFree(ctx->d_ref_of); cudaFree(ctx->d_pos_of);
     cudaFree(ctx->d_ctr); cudaFree(ctx->d_len_hist); cudaFree(ctx->d_todo[0]); cudaFree(ctx->d_todo[1]);
@@ -678,8 +678,12 @@ static int annotate_impl(mirge_ctx *ctx)
         const u32 *todo_in = r == 0 ? nullptr : ctx->d_todo[(r - 1) & 1];
         const u64 *n_in = r == 0 ? ctx->d_ctr : ctx->d_todo_n + r;
         ProfScope ps(ctx, KID_K2_ROUND0 + r);
-        k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
-                                            ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
+        if (rs.param > 0 && rs.lib == MIRGE_LIB_MIRNA)      // several seeds over consecutive table sizes: balance them
+            k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+                                                      ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
+        else
+            k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
     }
     CK(cudaGetLastError());
     ctx->annotated = true; ctx->tallied = false;
@@ -849,8 +853,8 @@ int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint
     if (rc) return rc;
     if (cap_records < U) return fail(ctx, MIRGE_E_ARG, "mirge_export_records_device: buffer too small");
     cudaStream_t st = ctx->stream;
-    u64 *d_cnt = nullptr;
-    CK(cudaMalloc(&d_cnt, 2 * (size_t)n_parts * sizeof(u64)));
+    if (!ctx->d_part) CK(cudaMalloc(&ctx->d_part, 2 * 1024 * sizeof(u64)));      // kept: cudaFree would synchronise the device every step
+    u64 *d_cnt = ctx->d_part;
     CK(cudaMemsetAsync(d_cnt, 0, 2 * (size_t)n_parts * sizeof(u64), st));
     const int rb = mirge_record_bytes(ctx), g = grid_for(U, 128, 148 * 8);
     {
@@ -867,7 +871,6 @@ int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint
     }
     CK(cudaMemcpyAsync(part_counts, d_cnt, (size_t)n_parts * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(d_cnt);
     CK(cudaGetLastError());
     return MIRGE_OK;
 }

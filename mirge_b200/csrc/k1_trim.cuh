@@ -73,60 +73,6 @@ __device__ __forceinline__ bool entry_key_equal(const TEntry<W> *e, const PSeq<W
     return eq;
 }
 
-// Find or insert `key` (already truncated to len bases); returns its dense id,
-// or 0xFFFFFFFF when the table or the id space is exhausted (err flag set).
-template <int W>
-__device__ u32 table_upsert(const TableView<W> &T, const PSeq<W> &key, int len, u64 h)
-{
-    const u32 want = (((((u32)(h >> 41)) & 0x7FFFFFu) | 1u) << 9) | ((u32)len << 1);   // busy form (ready bit clear)
-    u64 slot = h & T.mask;
-    for (u64 probe = 0; probe <= T.mask; probe++) {
-        TEntry<W> *e = T.slots + slot;
-        u32 *tagp = &e->tag;
-        u32 t = ld_acquire_u32(tagp);
-        if (t == 0) {
-            u32 old = atomicCAS(tagp, 0u, want);
-            if (old == 0) {
-                // dense ids come from ONE global counter: lanes inserting at the same time take a block of ids together
-                cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
-                u64 id = 0;
-                if (g.thread_rank() == 0) id = atomicAdd(T.n_unique, (u64)g.size());
-                id = g.shfl(id, 0) + g.thread_rank();
-                u32 id32 = 0xFFFFFFFFu;
-                if (id < T.max_unique) {
-                    id32 = (u32)id;
-#pragma unroll
-                    for (int w = 0; w < W; w++) T.useq[id * W + w] = key.s[w];
-#pragma unroll
-                    for (int w = 0; w < W / 2; w++) T.unmask[id * (W / 2) + w] = key.nm[w];
-                    T.ulen[id] = (u8)len;
-                } else {
-                    atomicOr(T.err, ERRF_FULL);
-                }
-#pragma unroll
-                for (int w = 0; w < W; w++) e->s[w] = key.s[w];
-#pragma unroll
-                for (int w = 0; w < W / 2; w++) e->nm[w] = key.nm[w];
-                e->id = id32;
-                st_release_u32(tagp, want | 1u);      // publish
-                return id32;
-            }
-            t = old;
-        }
-        if ((t | 1u) == (want | 1u)) {
-            while (!(t & 1u)) t = ld_acquire_u32(tagp);   // another thread is publishing this slot
-            if (entry_key_equal<W>(e, key)) {
-                u32 id;
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(id) : "l"(&e->id) : "memory");
-                return id;
-            }
-        }
-        slot = (slot + 1) & T.mask;
-    }
-    atomicOr(T.err, ERRF_FULL);
-    return 0xFFFFFFFFu;
-}
-
 // Warp-collective find-or-insert + count (the collapse of quantReads.py:9-16): every
 // lane of a converged warp calls it; lanes with `active` hold a key to be counted once.
 //   1. duplicates inside the warp are folded first (__match_any_sync on the 64-bit hash,
@@ -143,7 +89,7 @@ __device__ __forceinline__ void table_prefetch(const TableView<W> &T, u64 h)
     asm volatile("prefetch.global.L2 [%0];" :: "l"(T.slots + (h & T.mask)));
 }
 
-template <int W>
+template <int W, bool FOLD = true>
 __device__ __forceinline__ void table_find_warp(const TableView<W> &T, const PSeq<W> &key, int len, bool active, u64 h,
                                                 bool &lead_out, u32 &id_out, u32 &cnt_out)
 {
@@ -152,17 +98,21 @@ __device__ __forceinline__ void table_find_warp(const TableView<W> &T, const PSe
     lead_out = false; id_out = 0xFFFFFFFFu; cnt_out = 0;
     const unsigned act = __ballot_sync(0xffffffffu, active);
     if (!act) return;
-    const unsigned grp = __match_any_sync(0xffffffffu, h) & act;
-    const int leader = active ? (__ffs(grp) - 1) : (int)lane;
-    bool same = (__shfl_sync(0xffffffffu, len, leader) == len);
+    bool lead = active;
+    u32 cnt = 1u;
+    if (FOLD) {
+        const unsigned grp = __match_any_sync(0xffffffffu, h) & act;
+        const int leader = active ? (__ffs(grp) - 1) : (int)lane;
+        bool same = (__shfl_sync(0xffffffffu, len, leader) == len);
 #pragma unroll
-    for (int w = 0; w < W; w++) same = same && (__shfl_sync(0xffffffffu, key.s[w], leader) == key.s[w]);
+        for (int w = 0; w < W; w++) same = same && (__shfl_sync(0xffffffffu, key.s[w], leader) == key.s[w]);
 #pragma unroll
-    for (int w = 0; w < W / 2; w++) same = same && (__shfl_sync(0xffffffffu, key.nm[w], leader) == key.nm[w]);
-    const unsigned folded = __ballot_sync(0xffffffffu, active && same);
-    // a 64-bit hash collision between different keys of one warp: the odd lane inserts on its own
-    const bool lead = active && ((int)lane == leader || !same);
-    const u32 cnt = ((int)lane == leader) ? (u32)__popc(grp & folded) : 1u;
+        for (int w = 0; w < W / 2; w++) same = same && (__shfl_sync(0xffffffffu, key.nm[w], leader) == key.nm[w]);
+        const unsigned folded = __ballot_sync(0xffffffffu, active && same);
+        // a 64-bit hash collision between different keys of one warp: the odd lane inserts on its own
+        lead = active && ((int)lane == leader || !same);
+        cnt = ((int)lane == leader) ? (u32)__popc(grp & folded) : 1u;
+    }
     const u32 want = (((((u32)(h >> 41)) & 0x7FFFFFu) | 1u) << 9) | ((u32)len << 1);   // busy form (ready bit clear)
     u64 slot = h & T.mask;
     u64 probes = 0;
@@ -366,18 +316,29 @@ template <int W>
 __global__ void __launch_bounds__(128)
 k1_import_records(const unsigned char *__restrict__ buf, u64 n_records, int rec_bytes, TableView<W> T)
 {
-    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_records; r += (u64)gridDim.x * blockDim.x) {
-        const u64 *q = reinterpret_cast<const u64 *>(buf + r * (u64)rec_bytes);
+    for (u64 r0 = (u64)blockIdx.x * blockDim.x; r0 < n_records; r0 += (u64)gridDim.x * blockDim.x) {
+        const u64 r = r0 + threadIdx.x;
+        const bool on = r < n_records;
         PSeq<W> p;
 #pragma unroll
-        for (int w = 0; w < W; w++) p.s[w] = q[w];
+        for (int w = 0; w < W; w++) p.s[w] = 0;
 #pragma unroll
-        for (int w = 0; w < W / 2; w++) p.nm[w] = q[W + w];
-        const u32 *c = reinterpret_cast<const u32 *>(q + W + W / 2);
-        const int len = (int)c[0];
-        const u64 h = pseq_hash<W>(p, len);
-        const u32 id = table_upsert<W>(T, p, len, h);
-        if (id != 0xFFFFFFFFu)
+        for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
+        const u32 *c = nullptr;
+        int len = 0;
+        if (on) {
+            const u64 *q = reinterpret_cast<const u64 *>(buf + r * (u64)rec_bytes);
+#pragma unroll
+            for (int w = 0; w < W; w++) p.s[w] = q[w];
+#pragma unroll
+            for (int w = 0; w < W / 2; w++) p.nm[w] = q[W + w];
+            c = reinterpret_cast<const u32 *>(q + W + W / 2);
+            len = (int)c[0];
+        }
+        // records of one sender are distinct; the same key arrives from several senders in different warps
+        bool lead; u32 id, cnt;
+        table_find_warp<W, false>(T, p, len, on, on ? pseq_hash<W>(p, len) : 0ull, lead, id, cnt);
+        if (lead)
             for (int s = 0; s < T.S; s++) if (c[1 + s]) atomicAdd(&T.counts[(u64)id * T.S + s], c[1 + s]);
     }
 }

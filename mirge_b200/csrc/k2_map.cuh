@@ -188,151 +188,21 @@ __device__ __forceinline__ Query<W> query_bcast(const Query<W> &q, int src)
 // expensive sequence does not serialise its warp.  todo_in == nullptr means
 // the identity list 0 .. *n_in-1.  Sequences that stay un-annotated (filtered
 // out by length, or without a valid placement) are appended to todo_out.
-template <int W>
-__global__ void __launch_bounds__(128)
-k2_round(K2Arrays A, const u32 *__restrict__ todo_in, const u64 *__restrict__ n_in_ptr,
-         u32 *__restrict__ todo_out, u64 *__restrict__ n_out_ptr, LibView L, RoundParams R,
-         u64 *__restrict__ stat_processed, u64 *__restrict__ stat_aligned)
-{
-    const u64 n_in = *n_in_ptr;
-    const unsigned lane = threadIdx.x & 31;
-    u32 my_proc = 0, my_aln = 0;
-    const int nseeds = R.param + 1;
-    WarpQ wq = {0, 0};
-    for (u64 base = (u64)blockIdx.x * blockDim.x; base < n_in; base += (u64)gridDim.x * blockDim.x) {
-        const u64 i = base + threadIdx.x;
-        u32 id = WARPQ_NONE;
-        if (i < n_in) id = todo_in ? todo_in[i] : (u32)i;
-        const bool active = id != WARPQ_NONE;                // lists hold padding (common.cuh:warpq_slot)
-        bool pass = false;
-        Query<W> q;
-        q.n = 0;
-#pragma unroll
-        for (int w = 0; w < W; w++) { q.s[w] = 0; q.n2[w] = 0; q.len2[w] = 0; }
-        if (active) {
-            const int len = A.ulen[id];
-            pass = L.seq != nullptr;
-            if (R.len_filter < 0 && !(len < -R.len_filter)) pass = false;
-            if (R.len_filter > 0 && !(len > R.len_filter)) pass = false;
-            if (pass) {
-                PSeq<W> p;
-                int n = 0;
-#pragma unroll
-                for (int w = 0; w < W; w++) p.s[w] = A.useq[(u64)id * W + w];
-#pragma unroll
-                for (int w = 0; w < W / 2; w++) p.nm[w] = A.unmask[(u64)id * (W / 2) + w];
-                if (R.polyT) {
-                    int t = 0;
-                    while (t < len && pseq_base<W>(p, len - 1 - t) == 3 && !pseq_isn<W>(p, len - 1 - t)) t++;
-                    n = len - t;
-                    if (t < 3 || n < 11) pass = false;
-                    else pseq_truncate<W>(p, n);
-                } else {
-                    n = len - R.trim5 - R.trim3;
-                    if (n <= 0) pass = false;
-                    else { pseq_shift<W>(p, R.trim5); pseq_truncate<W>(p, n); }
-                }
-                if (pass) {
-                    q.n = n;
-#pragma unroll
-                    for (int w = 0; w < W; w++) {
-                        q.s[w] = p.s[w];
-                        q.n2[w] = spread32((u32)(p.nm[w >> 1] >> ((w & 1) * 32)));
-                        const int lo = w * 32;
-                        q.len2[w] = (n <= lo) ? 0ull : (n >= lo + 32) ? 0x5555555555555555ull
-                                                                       : (0x5555555555555555ull & ((1ull << ((n - lo) * 2)) - 1ull));
-                    }
-                }
-            }
-        }
-        u64 best = ~0ull;
-        int ti = -1;
-        if (pass) {
-            my_proc++;
-            const int region = (R.mode == 0) ? (q.n < 28 ? q.n : 28) : q.n;
-            const int maxk = region / nseeds;
-            for (int t = 0; t < R.ntabs; t++) if (R.tabs[t].k <= maxk) ti = t;
-            if (ti < 0) {
-                // no seed table short enough (only with a non-default min_length): scan every offset
-                for (u64 g = 0; g + (u64)q.n <= (u64)L.total; g++) consider<W>(L, q, (u32)g, R, best);
-            }
-        }
-        for (int sd = 0; sd < nseeds; sd++) {           // warp-uniform trip count
-            u32 lo = 0, hi = 0;
-            int so = 0;
-            if (pass && ti >= 0) {
-                const KmerTab T = R.tabs[ti];
-                const u64 kmask = (T.k == 32) ? ~0ull : ((1ull << (2 * T.k)) - 1ull);
-                so = sd * T.k;
-                if (!(words_window64<W>(q.n2, so) & kmask)) {   // a seed holding N cannot match exactly
-                    const u32 code = (u32)(words_window64<W>(q.s, so) & kmask);
-                    lo = __ldg(T.bucket_off + code); hi = __ldg(T.bucket_off + code + 1);
-                }
-            }
-            const u32 cnt = hi - lo;
-            if (cnt && cnt < K2_HEAVY) {
-                const KmerTab T = R.tabs[ti];
-                for (u32 x = lo; x < hi; x++) {
-                    const u32 ppos = __ldg(T.pos + x);
-                    if (ppos >= (u32)so) consider<W>(L, q, ppos - (u32)so, R, best);
-                }
-            }
-            unsigned heavy = __ballot_sync(0xffffffffu, cnt >= K2_HEAVY);
-            while (heavy) {
-                const int src = __ffs(heavy) - 1;
-                heavy &= heavy - 1;
-                const Query<W> qb = query_bcast<W>(q, src);
-                const u32 blo = __shfl_sync(0xffffffffu, lo, src), bhi = __shfl_sync(0xffffffffu, hi, src);
-                const int bso = __shfl_sync(0xffffffffu, so, src), bti = __shfl_sync(0xffffffffu, ti, src);
-                const u32 *pos = R.tabs[bti].pos;
-                u64 lb = ~0ull;
-                for (u32 x = blo + lane; x < bhi; x += 32) {
-                    const u32 ppos = __ldg(pos + x);
-                    if (ppos >= (u32)bso) consider<W>(L, qb, ppos - (u32)bso, R, lb);
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const u64 o = __shfl_xor_sync(0xffffffffu, lb, d);
-                    lb = o < lb ? o : lb;
-                }
-                if ((int)lane == src && lb < best) best = lb;
-            }
-        }
-        bool hit = false;
-        if (pass && best != ~0ull) {
-            hit = true;
-            const u32 g = R.highest ? ~(u32)best : (u32)best;
-            const int r = ref_of_gpos(L, g);
-            A.round_of[id] = (signed char)(R.round + 1);
-            A.ref_of[id] = r;
-            A.pos_of[id] = (int)(g - __ldg(L.ref_off + r));
-            A.mm_of[id] = (signed char)(best >> 32);
-            my_aln++;
-        }
-        const bool push = active && !hit;
-        if (R.chunked) {
-            const u64 at = warpq_slot(push, n_out_ptr, todo_out, wq);
-            if (push) todo_out[at] = id;
-        } else {
-            const unsigned bal = __ballot_sync(0xffffffffu, push);
-            if (bal) {
-                const int leader = __ffs(bal) - 1;
-                u64 b0 = 0;
-                if ((int)lane == leader) b0 = atomicAdd(n_out_ptr, (u64)__popc(bal));
-                b0 = __shfl_sync(0xffffffffu, b0, leader);
-                if (push) todo_out[b0 + __popc(bal & ((1u << lane) - 1u))] = id;
-            }
-        }
-    }
-    warpq_close(todo_out, wq);
-    // per-warp statistics
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        my_proc += __shfl_down_sync(0xffffffffu, my_proc, d);
-        my_aln += __shfl_down_sync(0xffffffffu, my_aln, d);
-    }
-    if (lane == 0) {
-        if (my_proc) atomicAdd(stat_processed, (u64)my_proc);
-        if (my_aln) atomicAdd(stat_aligned, (u64)my_aln);
-    }
-}
+// BAL (the multi-seed rounds on the miRNA library, whose seed tables have consecutive sizes): the seeds share the
+// region's spare bases, so the first ones are one base longer.  Those rounds work out of L1 and are issue
+// bound, so they are held to 8 CTAs per SM; the plain rounds wait on random library reads and keep the
+// compiler's natural register budget (a forced cap serialises the loads of a verification: +40 % time).
+#define K2_ROUND_NAME k2_round
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128)
+#define K2_BAL 0
+#include "k2_round.inc"
+#undef K2_ROUND_NAME
+#undef K2_LAUNCH_BOUNDS
+#undef K2_BAL
+#define K2_ROUND_NAME k2_round_balanced
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, 8)
+#define K2_BAL 1
+#include "k2_round.inc"
+#undef K2_ROUND_NAME
+#undef K2_LAUNCH_BOUNDS
+#undef K2_BAL
