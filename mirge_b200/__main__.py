@@ -4,8 +4,8 @@ src/mirge/__main__.py:73-392), served by the CUDA pipeline.
 Same flags, same library-directory layout, same output directory
 `<-o>/miRge.<YYYY-MM-DD_HH-MM-SS>/` and table files.  `-pb` (bowtie directory)
 and `-cpu` are accepted and ignored: no bowtie or cutadapt process is started.
-Only the annotate sub-command exists; -gff / -ai / -trf outputs are not produced
-(DESIGN.md "Out of scope").
+Only the annotate sub-command exists; -gff writes <sample>_isomiRs.gff (mirge_b200/gff.py); -ai / -trf outputs
+are not produced (DESIGN.md "Out of scope").
 """
 import argparse
 import os
@@ -88,11 +88,12 @@ def main(argv=None):
         adapter = 'TGGAATTCTCGGGTGCCAAGGAACTCCAG'      # __main__.py:124-125
     elif adapter == 'ion':
         adapter = '11'                                  # __main__.py:126-127 (cutadapt rejects it: starts with a digit)
-    for flag, name in ((args.a_to_i, '-ai'), (args.gff_output, '-gff'), (args.trf_output, '-trf')):
+    for flag, name in ((args.a_to_i, '-ai'), (args.trf_output, '-trf')):
         if flag:
             print('warning: %s output is not produced by this build' % name, file=sys.stderr)
 
     from .libs import LibraryError
+    from .gff import GffError
     from .pipeline import AnnotateRun
     from .tables import ZeroMiRNAError
     from .engine import MirgeError
@@ -103,12 +104,14 @@ def main(argv=None):
     try:
         run = AnnotateRun(samples, args.libraryPath, args.species, db, adapter, args.spikeIn,
                           max_unique=args.max_unique, device=args.gpu)
+        if args.gff_output and not os.path.isfile(run.libdir.gff3):     # extractPreMiRName opens it unguarded (IOError upstream)
+            raise LibraryError('%s does not exist: -gff needs the miRNA coordinate file.' % run.libdir.gff3)
         os.mkdir(outdir)
         run.run()
         t1 = time.time()
         print('Summarizing and tabulating results...')
-        run.write_outputs(outdir, args.canoRatio, tcf=args.trimmed_collapsed_fa, isomir_diff=args.diff_isomirs)
-    except LibraryError as e:
+        run.write_outputs(outdir, args.canoRatio, tcf=args.trimmed_collapsed_fa, isomir_diff=args.diff_isomirs, gff=args.gff_output)
+    except (LibraryError, GffError) as e:
         print(str(e))
         sys.exit(1)
     except ZeroMiRNAError as e:

@@ -4,6 +4,7 @@
                                     snorna,rrna,ncrna_others,spike-in}.*.ebwt
     <lib>/<species>/fasta.Libs/<sp>_mirna_SNP_pseudo_<DB>.fa
     <lib>/<species>/annotation.Libs/<sp>_merges_<DB>.csv
+    <lib>/<species>/annotation.Libs/<sp>_<DB>.gff3                  (-gff only)
 
 The reference hands the `.ebwt` indexes to bowtie.  The CUDA mapper needs the
 reference sequences themselves, so next to every index it expects
@@ -50,6 +51,7 @@ class LibraryDir:
         self.index_path = os.path.join(library_path, species, 'index.Libs')
         self.mirna_fa = os.path.join(library_path, species, 'fasta.Libs', '%s_mirna_SNP_pseudo_%s.fa' % (species, db))
         self.merges_csv = os.path.join(library_path, species, 'annotation.Libs', '%s_merges_%s.csv' % (species, db))
+        self.gff3 = os.path.join(library_path, species, 'annotation.Libs', '%s_%s.gff3' % (species, db))     # __main__.py:150
         self.types = list(REQUIRED) + (['spike-in'] if spike_in else [])
 
     def index_base(self, t):

@@ -12,6 +12,7 @@ import time
 
 import numpy as np
 
+from . import gff as gff_mod
 from . import tables
 from .engine import Engine, LIB_IDS, MirgeError
 from .libs import LibraryDir
@@ -134,7 +135,7 @@ class AnnotateRun:
                 self.log('unique-sequence table full; retrying with max_unique=%d' % self.max_unique)
 
     # -- outputs ------------------------------------------------------------------
-    def write_outputs(self, outdir, cano_ratio='0.1', tcf=False, isomir_diff=False):
+    def write_outputs(self, outdir, cano_ratio='0.1', tcf=False, isomir_diff=False, gff=False):
         """summarize -> miRNAmerge -> filter -> generateReport / writeDataToCSV (__main__.py:381-389)."""
         e = self.engine
         p, k, _ = e.stats()
@@ -161,4 +162,10 @@ class AnnotateRun:
             f.write(tables.mir_rpm_csv(self.sample_names, logDic, mirDic))
         if tcf:
             tables.write_trim_collapse_fa(outdir, uniq, self.sample_names)
+        if gff:     # <sample>_isomiRs.gff (writeDataToCSV.py:621-646)
+            pre_of = gff_mod.stem_loop_names(self.libdir.gff3, self.libdir.db)
+            mir_names, mir_seqs = self.libdir.load('mirna')
+            hp_names, hp_seqs = self.libdir.load('hairpin')
+            recs = gff_mod.gff_rows(uniq, mir_names, mir_seqs, hp_names, hp_seqs, pre_of, self.libdir.db)
+            gff_mod.write_gff(outdir, recs, self.sample_names, self.libdir.db)
         return dict(logDic=logDic, mirDic=mirDic, len_hist=t['len_hist'])

@@ -514,3 +514,279 @@ def isomir_tables(seqDic, sampleList, logDic):
                 isomirOut.append(py2_str_float(topIsomir))
                 out2.append(','.join(isomirOut) + '\n')
     return ''.join(out1), ''.join(out2)
+
+
+# --------------------------------------------------------------------------
+# -gff: <sample>_isomiRs.gff, literal restatement
+# --------------------------------------------------------------------------
+NT2CODE = dict(zip(                                           # runAnnotationPipeline.py:613-620
+    [a + b + c for a in 'ACGT' for b in 'ACGT' for c in 'ACGT'],
+    '@fcoladsmkhwgebpvtDnx#yiCEGSrjqHT84FVXZ6KM$AWY35LNJzU9P07IuBQOR%'))
+
+
+def extract_pre_mir_name(gff3_text, miRNA_database):
+    """extractPreMiRName.py:9-62: miRNA name -> stem-loop name from <species>_<DB>.gff3."""
+    def pickOptimal(names):                                   # :9-17
+        tails = [n.split('-')[-1] for n in names]
+        if all(t.isdigit() for t in tails):
+            cand = [[int(tails[i]), names[i]] for i in range(len(names))]
+        else:
+            cand = [[names[i]] for i in range(len(names))]
+        cand.sort()
+        return cand[0][-1]
+
+    out = {}
+    if miRNA_database == 'miRBase':
+        cor, order, loopName = {}, [], {}
+        for line in gff3_text.splitlines(True):
+            if line[0] != '#':
+                c = line.strip().split('\t')
+                if c[2] == 'miRNA':
+                    name = c[-1].split('Name=')[1].split(';')[0].strip()
+                    loop = c[-1].split('Derives_from=')[1].split(';')[0].strip()
+                    if name not in order:
+                        order.append(name)
+                        cor[name] = {loop: (c[0], c[6], int(c[3]) - 1, int(c[4]) - 1)}
+                    else:
+                        cor[name][loop] = (c[0], c[6], int(c[3]) - 1, int(c[4]) - 1)
+                if c[2] == 'miRNA_primary_transcript':
+                    alias = c[-1].split('Alias=')[1].split(';')[0].strip()
+                    loopName[alias] = c[-1].split('Name=')[1].split(';')[0].strip()
+        for name in order:
+            if len(cor[name]) > 1:
+                out[name] = pickOptimal([loopName[k] for k in cor[name].keys()])
+            else:
+                out[name] = loopName[list(cor[name].keys())[0]]
+    else:
+        for line in gff3_text.splitlines(True):
+            if line[0] != '#':
+                c = line.strip().split('\t')
+                if c[2] == 'miRNA':
+                    name = c[-1].split('ID=')[1].split(';')[0].strip()
+                    out[name] = '_'.join(name.split('_')[:-1]) + '_pre'
+    return out
+
+
+def infer_pre_mir_name(canon, pre_of, miRNA_database):
+    """runAnnotationPipeline.py:353-380."""
+    if canon in pre_of:
+        return pre_of[canon]
+    if miRNA_database == 'miRBase':
+        stem = '-'.join(canon.split('-')[:-1])
+        for k in (stem, stem + '-5p', stem + '-3p'):
+            if k in pre_of:
+                return pre_of[k]
+        return canon.replace('-5p', '').replace('-3p', '').replace('miR', 'mir')
+    return canon.replace('_5p*', '').replace('_3p*', '').replace('_5p', '').replace('_3p', '') + '_pre'
+
+
+def _ldash(s):
+    return len(s) - len(s.lstrip('-'))
+
+
+def _rdash(s):
+    return len(s) - len(s.rstrip('-'))
+
+
+def fill_terminal(pre, lib, mir, read, start, indexValue):
+    """fillTerminal, runAnnotationPipeline.py:86-172: pad the hairpin, the library entry, the mature and the read
+    with '-' so that they line up column by column."""
+    if mir not in pre:                                        # .index() raising ValueError (:159-164)
+        return '', '', '', '', False
+    at = pre.index(mir)
+    if at + len(mir) + 6 > len(pre):
+        pre = pre + '-' * (at + len(mir) + 6 - len(pre))
+    else:
+        lib = lib + '-' * (len(pre) - at - len(mir) - 6)
+    if at < 2:
+        pre = '-' * (2 - at) + pre
+    else:
+        lib = '-' * (at - 2) + lib
+    at2 = pre.index(mir)
+    mir = '-' * at2 + mir + '-' * (len(pre) - at2 - len(mir))
+    if indexValue == 0:                                       # exact miRNA hit: the read sits at 1-based `start` of the entry
+        head, i = '', 0
+        for ch in lib:
+            if ch == '-':
+                head += '-'
+            else:
+                i += 1
+                if i == start:
+                    break
+                head += '-'
+        read = head + read
+        read = read + '-' * (len(lib) - len(read))
+    else:                                                     # isomiR round: bowtie saw read[1:-2]
+        room = len(lib) - _ldash(lib) - start + 1
+        if len(read) - 1 > room:
+            extra = len(read) - 1 - room
+            lib, pre, mir = lib + '-' * extra, pre + '-' * extra, mir + '-' * extra
+        else:
+            read = read + '-' * (room - len(read) + 1)
+        if start - 1 + _ldash(lib) < 1:
+            pad = 1 - start + 1 - _ldash(lib)
+            pre, mir, lib = '-' * pad + pre, '-' * pad + mir, '-' * pad + lib
+        else:
+            read = '-' * (start - 1 + _ldash(lib) - 1) + read
+    return pre, lib, mir, read, True
+
+
+def make_cigar(seq, mature):
+    """make_cigar, runAnnotationPipeline.py:180-212 (runs of M are counted, everything else stays one character)."""
+    raw = ''
+    for a, b in zip(seq, mature):
+        if a == b:
+            raw += 'M'
+        elif a != '-' and b != '-':
+            raw += a
+        elif a == '-':
+            raw += 'D'
+        else:
+            raw += 'I'
+    short, cache, counter = '', '', 1
+    for c in raw:
+        if c != cache and cache != '' and cache == 'M':
+            short += 'M' if counter == 1 else str(counter) + 'M'
+            counter = 1
+            cache = c
+        if c != 'M':
+            short += c
+        if c == cache and c == 'M':
+            counter += 1
+        cache = c
+    if cache == 'M':
+        short += 'M' if counter == 1 else str(counter) + 'M'
+    return short
+
+
+def make_id(seq):
+    """make_id, runAnnotationPipeline.py:214-235."""
+    start, uid, i = 0, '', 0
+    for i in range(0, len(seq) + 1, 3):
+        if i == 0:
+            continue
+        tri = seq[start:i]
+        if tri not in NT2CODE:
+            uid = '.'
+            break
+        uid += NT2CODE[tri]
+        start = i
+    if len(seq) > i and uid != '.':
+        dummy = 'A' * (3 - (len(seq) - i))
+        tri = seq[i:len(seq)] + dummy
+        if tri in NT2CODE:
+            uid += NT2CODE[tri] + str(len(dummy))
+        else:
+            uid = '.'
+    return uid
+
+
+def analyze_alignment(pre, lib, mir, read):
+    """analyzeAlignment, runAnnotationPipeline.py:237-339 -> (type, variant, pre_start, pre_end, cigar)."""
+    assert len({len(pre), len(lib), len(mir), len(read)}) == 1
+    variants = []
+    if mir == read:
+        kind = 'ref_miRNA'
+        variants.append('NA')
+    else:
+        kind = 'isomiR'
+        s1, e1 = _ldash(mir), len(mir) - _rdash(mir)
+        snp, snp_pos = False, ''
+        for i in range(s1, e1):
+            if read[i] != '-' and read[i] != mir[i]:
+                snp = True
+                if 1 <= i <= 6:
+                    snp_pos = '_seed'
+                elif i == 7:
+                    snp_pos = '_central_offset'
+                elif 8 <= i <= 11:
+                    snp_pos = '_central'
+                elif 12 <= i <= 16:
+                    snp_pos = 'central_supp'
+                else:
+                    snp_pos = ''
+                break
+        p5 = add = p3 = False
+        p5_pos = add_pos = p3_pos = ''
+        if _ldash(read) > _ldash(mir):
+            p5, p5_pos = True, str(_ldash(mir) - _ldash(read))
+        elif _ldash(read) < _ldash(mir):
+            a = _ldash(read)
+            if read[a:s1] != pre[a:s1]:
+                snp, snp_pos = True, ''
+            p5, p5_pos = True, '+' + str(_ldash(mir) - _ldash(read))
+        if _rdash(read) > _rdash(mir):
+            p3, p3_pos = True, str(_rdash(mir) - _rdash(read))
+        elif _rdash(read) < _rdash(mir):
+            z = len(read) - _rdash(read) - 1
+            if read[e1:z + 1] != pre[e1:z + 1]:
+                add, add_pos = True, '+' + str(_rdash(mir) - _rdash(read))
+            else:
+                p3, p3_pos = True, '+' + str(_rdash(mir) - _rdash(read))
+        if snp:
+            variants.append('iso_snp' + snp_pos)
+        if add:
+            variants.append('iso_add:' + add_pos)
+        if p5:
+            variants.append('iso_5p:' + p5_pos)
+        if p3:
+            variants.append('iso_3p:' + p3_pos)
+    if _ldash(pre) > 0:
+        if _ldash(read) >= _ldash(pre):
+            pre_start = _ldash(read) - _ldash(pre) + 1
+        else:
+            pre_start = 1 - (_ldash(pre) - _ldash(read))
+    else:
+        pre_start = _ldash(read) + 1
+    pre_end = pre_start + len(read) - _ldash(read) - _rdash(read) - 1
+    a, z = _ldash(read), len(read) - _rdash(read) - 1
+    return kind, ','.join(variants), pre_start, pre_end, make_cigar(read[a:z + 1], pre[a:z + 1])
+
+
+def gff_literal(seqDic, hits, sampleList, mirna_lib, hairpin_lib, pre_of, miRNA_database):
+    """What runAnnotationPipeline.py:643-655 (updateIsomiRDic / updateIsomiRDic2 after rounds 0 and 8) and
+    writeDataToCSV.py:621-646 leave in <sample>_isomiRs.gff.  hits: seq -> (round index 0 or 8, miRNA entry name,
+    1-based POS as bowtie reports it); mirna_lib / hairpin_lib: name -> sequence (`bowtie-inspect` output, :603-611).
+    Returns {sample: (header text, [row, ...])}; row order is Python-2 dict order upstream."""
+    content = {}
+    for rnd in (0, 8):
+        for seqKey, (r, name, pos) in hits.items():
+            if r != rnd:
+                continue
+            canon = name.split('.')[0] if '.' in name else name
+            content[seqKey] = {'miRName': name, 'preMiRName': infer_pre_mir_name(canon, pre_of, miRNA_database),
+                               'start': str(pos), 'cigar': (str(len(seqKey)) + 'M'), 'annot': 0, 'filter': 'Pass',
+                               'uid': make_id(seqKey)}
+        for seqKey in list(content.keys()):
+            e = content[seqKey]
+            if e['annot'] != 0:
+                continue
+            lib = mirna_lib[e['miRName']]
+            mir = lib[2:-6]
+            pre = hairpin_lib[e['preMiRName']]
+            if '.SNP' in e['miRName'] and '.SNPC' not in e['miRName']:
+                canon_lib = mirna_lib[e['miRName'].split('.')[0] + '.SNPC']
+                canon_mir = canon_lib[2:-6]
+                canon_pre = hairpin_lib[infer_pre_mir_name(e['miRName'].split('.')[0], pre_of, miRNA_database)]
+                at = canon_pre.index(canon_mir)               # ValueError = the reference's 'Error happens.' exit
+                pre = canon_pre[:at] + mir + canon_pre[at + len(mir):]
+            preO, libO, mirO, readO, ok = fill_terminal(pre, lib, mir, seqKey, int(e['start']), rnd)
+            if ok:
+                kind, variant, ps, pe, cigar = analyze_alignment(preO, libO, mirO, readO)
+                e.update(type=kind, pre_start=str(ps), pre_end=str(pe), variant=str(variant), strand='+', annot=1, cigar=cigar)
+            else:
+                del content[seqKey]
+    source = 'miRBase22' if miRNA_database == 'miRBase' else miRNA_database + '2.0'
+    out = {}
+    for i, sample in enumerate(sampleList):
+        sampleName = os.path.splitext(sample)[0]
+        header = '# GFF3 adapted for miRNA sequencing data\n## VERSION 0.0.1\n## source-ontology: %s\n## COLDATA: %s\n' % (source, sampleName)
+        rows = []
+        for seqKey, e in content.items():
+            n = seqDic[seqKey]['quant'][i]
+            if n >= 1:
+                rows.append('\t'.join([e['miRName'], source, e['type'], e['pre_start'], e['pre_end'], '.', e['strand'], '.']) + '\t' +
+                            ';'.join(['Read ' + seqKey, ' UID ' + e['uid'], ' Name ' + e['miRName'], ' Parent ' + e['preMiRName'],
+                                      ' Variant ' + e['variant'], ' Cigar ' + e['cigar'], ' Expression ' + str(n), ' Filter ' + e['filter']]) + '\n')
+        out[sample] = (header, rows)
+    return out

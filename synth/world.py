@@ -53,7 +53,9 @@ def _rand_seqs(rng, n, mean_len, jitter=0.2):
 class World:
     """All libraries as {type: (names, seqs)} plus the expressed-miRNA table."""
 
-    def __init__(self, seed=20180626, scale=1.0, species='synth', db='miRBase', n_expressed=400):
+    def __init__(self, seed=20180626, scale=1.0, species='synth', db='miRBase', n_expressed=400, snpc_names=False):
+        # snpc_names: a miRNA that has a SNP entry is itself named <name>.SNPC, as the reference's -gff code expects
+        # (runAnnotationPipeline.py:417-419); off by default so that fixtures and benchmarks keep their names
         rng = np.random.default_rng(np.random.PCG64(seed))
         self.species, self.db, self.seed = species, db, seed
         self.libs = {}
@@ -72,6 +74,7 @@ class World:
         hp_names = [f'{species}-mir-{i + 1}' for i in range(nh)]
         mir_names, mir_seqs, mature_seqs, merges = [], [], [], []
         self.mir_table = []   # (name, hairpin idx, mature start, mature len)
+        self.derives = []     # (canonical miRNA name, stem-loop name) for <sp>_<DB>.gff3
         for i in range(nh):
             h = hp_seqs[i]
             arms = ['5p']
@@ -89,15 +92,20 @@ class World:
                 mir_seqs.append(entry)
                 mature_seqs.append(h[st:st + ln])
                 self.mir_table.append((name, i, st, ln))
+                self.derives.append((name, hp_names[i]))
                 r = rng.random()
                 if r < 0.10:      # SNP variant of this entry (one substitution inside the mature)
                     p = 2 + int(rng.integers(1, ln - 1))
                     alt = 'ACGT'.replace(entry[p], '')[int(rng.integers(0, 3))]
                     sname = name + '.SNP1'
+                    cname = name
+                    if snpc_names:
+                        cname = name + '.SNPC'
+                        mir_names[-1] = cname
                     mir_names.append(sname)
                     mir_seqs.append(entry[:p] + alt + entry[p + 1:])
                     mature_seqs.append(mir_seqs[-1][2:2 + ln])
-                    merges.append(f'{name}/SNP1,{name},{sname}')
+                    merges.append(f'{name}/SNP1,{cname},{sname}')
                 elif r < 0.13:    # paralog: same mature, different flanks, on its own hairpin
                     left = ''.join('ACGT'[x] for x in rng.integers(0, 4, st))
                     right = ''.join('ACGT'[x] for x in rng.integers(0, 4, len(h) - st - ln))
@@ -107,6 +115,7 @@ class World:
                     mir_names.append(pname)
                     mir_seqs.append(hp_seqs[-1][st - 2:st + ln + 6])
                     mature_seqs.append(h[st:st + ln])
+                    self.derives.append((pname, hp_names[-1]))
                     merges.append(f'{species}-miR-{i + 1}/{i + 1}b-{arm},{name},{pname}')
         self.libs['hairpin'] = (hp_names, hp_seqs)
         self.libs['mirna'] = (mir_names, mir_seqs)
@@ -139,7 +148,22 @@ class World:
             f.write(''.join(f'>{n}\n{s}\n' for n, s in zip(self.libs['mirna'][0], self.mature_seqs)))
         with open(os.path.join(d, 'annotation.Libs', f'{sp}_merges_{db}.csv'), 'w') as f:
             f.write(''.join(m + '\n' for m in self.merges))
+        with open(os.path.join(d, 'annotation.Libs', f'{sp}_{db}.gff3'), 'w') as f:
+            f.write(self.gff3_text())
         return root
+
+    def gff3_text(self):
+        """<sp>_<DB>.gff3 in miRBase layout: one miRNA_primary_transcript per hairpin, one miRNA per mature."""
+        hp = self.libs['hairpin'][0]
+        alias = {n: 'MI%07d' % (k + 1) for k, n in enumerate(hp)}
+        out = ['##gff-version 3\n']
+        for k, n in enumerate(hp):
+            out.append('chr1\t.\tmiRNA_primary_transcript\t%d\t%d\t.\t+\t.\tID=%s;Alias=%s;Name=%s\n'
+                       % (1000 * k + 1, 1000 * k + len(self.libs['hairpin'][1][k]), alias[n], alias[n], n))
+        for k, (name, loop) in enumerate(self.derives):
+            out.append('chr1\t.\tmiRNA\t%d\t%d\t.\t+\t.\tID=MIMAT%07d;Alias=MIMAT%07d;Name=%s;Derives_from=%s\n'
+                       % (k + 1, k + 22, k + 1, k + 1, name, alias[loop]))
+        return ''.join(out)
 
     # -- FASTQ ------------------------------------------------------------------
     def _c_world(self):
