@@ -1,23 +1,27 @@
-// k1_kernel.cuh -- the fused trim + collapse kernel (K1).
+// k1_kernel.cuh -- K1: 3' adapter trim + length filter + collapse.
 //
 // Per read (one thread each, packed record streamed with one 128-bit load):
 //   1. apply the quality-trim window computed by K0;
 //   2. find the 3' adapter exactly as cutadapt would:
-//        fast path  - Myers' bit-vector edit distance (the <=32-nt adapter is one
-//                     machine word) gives the cost of EVERY DP cell of the last
-//                     columns; the few candidate end cells cutadapt ranks by
+//        prefilter  - exact comparisons plus host-proved dominance tables settle most
+//                     reads with no dynamic programming at all (k1_prefilter.cuh);
+//        class 1    - reads that only need the full-length cost scan (score-only
+//                     Myers columns);
+//        class 2    - general search: Myers' bit-vector edit distance (the <=32-nt
+//                     adapter is one machine word) gives the cost of EVERY DP cell of
+//                     the last columns; the few candidate end cells cutadapt ranks by
 //                     (matches, cost, visiting order) are resolved by walking
 //                     cutadapt's own predecessor preference (diagonal, then
 //                     insertion, then deletion) backwards until a zero-cost cell,
-//                     reading cell costs from the bit-vectors of the last 8
-//                     columns (kept in shared memory);
-//        slow path  - reads whose candidates cannot be settled inside that
-//                     window (sequencing errors deep inside the adapter, a full
-//                     inexact adapter occurrence, adapters > 32 nt) are queued
-//                     per CTA and run through the literal banded DP
-//                     (locate_back) by fully converged warps;
-//   3. length filter, then insert into the unique-sequence table.
-// Both paths return cutadapt's rstart; parity tests compare them read by read.
+//                     reading cell costs from the bit-vectors of the last 8 columns
+//                     (kept in shared memory);
+//        class 3    - reads whose candidates cannot be settled inside that window
+//                     (sequencing errors deep inside the adapter, a full inexact
+//                     adapter occurrence, adapters > 32 nt): the same search with all
+//                     columns kept, or the literal banded DP (locate_back);
+//   3. length filter, then warp-collective insert into the unique-sequence table.
+// The classes run as four kernels connected by device queues (end of this file).
+// Every path returns cutadapt's rstart; parity tests compare them read by read.
 #pragma once
 #include "common.cuh"
 #include "k1_trim.cuh"
