@@ -1,4 +1,5 @@
-// k1_trim.cuh -- K1: 3' adapter trim + length filter + collapse, one pass.
+// k1_trim.cuh -- K1 building blocks: the unique-sequence table (warp-collective upsert,
+// count cache), cutadapt's literal banded DP, the multi-GPU exchange records.
 //
 // Replaces, per read, the Worker.run modifier chain of utils/trim_file.py:52-55
 // (cutadapt AdapterCutter / UnconditionalCutter + min_length) and the dict
@@ -7,7 +8,6 @@
 // window); output is the device hash table of unique sequences with per-sample
 // counts, the read-length histogram and the kept counter.
 #pragma once
-#include <cooperative_groups.h>
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------
