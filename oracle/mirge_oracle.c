@@ -677,6 +677,82 @@ int orc_map_one(OrcCtx *c, int lib_id, const char *read, int n, int mode, int pa
     return 1;
 }
 
+/* ------------------------------------------------------------------ */
+/* genome passes -- both strands, every valid    */
+/* alignment enumerated (bowtie -a)                                        */
+/* ------------------------------------------------------------------ */
+
+/* Like verify_at with a configurable seed length (-l): mode 0 = "-n N" (at most N
+ * mismatches in the first min(seedlen, n) bases, 30 per mismatch against -e 70 overall),
+ * mode 1 = "-v V". */
+static int verify_at_l(const OrcLib *l, uint64_t g, const char *read, int n, int mode, int param, int seedlen, int *mm_out)
+{
+    if (g + (uint64_t)n > l->total) return 0;
+    int r = ref_of_gpos(l, g);
+    if (g + (uint64_t)n > l->off[r + 1]) return 0;
+    int mm_seed = 0, mm_total = 0;
+    for (int i = 0; i < n; i++) {
+        char rc = l->seq[g + i];
+        if (rc == 'N') return 0;
+        if (read[i] != rc) { mm_total++; if (i < seedlen) mm_seed++; if (mm_total > 3) return 0; }
+    }
+    if (mode == 0) { if (mm_seed > param || 30 * mm_total > 70) return 0; }
+    else { if (mm_total > param) return 0; }
+    *mm_out = mm_total;
+    return 1;
+}
+
+/* All alignments of read[0 : n - trim3] (bowtie -3) and, unless norc, of its reverse
+ * complement, against library lib_id: counts[k] = number of alignments with k mismatches
+ * (k = 0..3).  Uses:
+ *   writeDataToCSV.py:1260  `-n 1 -f -a -3 2`  A-to-I candidate reads against the genome; the caller keeps
+ *                           a read when its lowest occupied stratum holds exactly one alignment (:1273-1281)
+ *   writeDataToCSV.py:1488  `-n 0 -f -a -3 2`
+ *   __main__.py:538         `-n 0 -m 3 -l 25 -a --best` (unannotated reads, both strands; -m: reads with more
+ *                           than 3 alignments are suppressed -- sum(counts) > 3)
+ * A reverse-strand alignment is a forward alignment of the reverse complement: bowtie's seed (the read's 5'
+ * end) then sits at the RIGHT end of the window, so the seed test applies to the revcomp's LAST seedlen bases.
+ * Exhaustive scan (test oracle: small genomes only). */
+int orc_map_genome_all(OrcCtx *c, int lib_id, const char *read, int n, int mode, int param, int seedlen, int trim3,
+                       int norc, uint32_t counts[4])
+{
+    OrcLib *l = (lib_id >= 0 && lib_id < ORC_MAX_LIBS) ? c->libs[lib_id] : NULL;
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    n -= trim3;
+    if (!l || n <= 0) return 0;
+    char fw[n + 1], rc[n + 1];
+    for (int i = 0; i < n; i++) {
+        char ch = (char)toupper((unsigned char)read[i]);
+        fw[i] = (base2(ch) >= 0) ? ch : 'N';
+    }
+    for (int i = 0; i < n; i++) {
+        char ch = fw[n - 1 - i];
+        rc[i] = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N';
+    }
+    int sl = seedlen < n ? seedlen : n;
+    uint32_t total = 0;
+    for (uint64_t g = 0; g + (uint64_t)n <= l->total; g++) {
+        int mm;
+        if (verify_at_l(l, g, fw, n, mode, param, sl, &mm)) { counts[mm]++; total++; }
+        if (!norc) {
+            /* seed = last sl bases of the window: count seed mismatches there */
+            int r = ref_of_gpos(l, g);
+            if (g + (uint64_t)n > l->off[r + 1]) continue;
+            int mm_seed = 0, mm_total = 0, bad = 0;
+            for (int i = 0; i < n; i++) {
+                char ref = l->seq[g + i];
+                if (ref == 'N') { bad = 1; break; }
+                if (rc[i] != ref) { mm_total++; if (i >= n - sl) mm_seed++; if (mm_total > 3) { bad = 1; break; } }
+            }
+            if (bad) continue;
+            if (mode == 0) { if (mm_seed > param || 30 * mm_total > 70) continue; }
+            else { if (mm_total > param) continue; }
+            counts[mm_total]++; total++;
+        }
+    }
+    return (int)total;
+}
+
 /* Round table, runAnnotationPipeline.py:574-599.  lib ids:
  * 0 mirna 1 hairpin 2 mature_trna 3 pre_trna 4 snorna 5 rrna 6 ncrna_others
  * 7 mrna 8 (mirna again) 9 spike-in. */

@@ -67,6 +67,7 @@ def lib():
         L.orc_match_back.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_map_one.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_map_bruteforce.argtypes = L.orc_map_one.argtypes
+        L.orc_map_genome_all.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -225,6 +226,24 @@ class Oracle:
         f = lib().orc_map_bruteforce if brute else lib().orc_map_one
         ok = f(self.h, lib_id, read.encode(), len(read), mode, param, int(highest), _p(r[0:1]), _p(r[1:2]), _p(r[2:3]))
         return (int(r[0]), int(r[1]), int(r[2])) if ok else None
+
+    def genome_hits(self, lib_id, read, mode, param, seedlen=28, trim3=0, norc=False):
+        """Alignments of read (minus trim3 3' bases) on both strands of library lib_id, per mismatch count 0..3
+        (bowtie -a)."""
+        cnt = np.zeros(4, np.uint32)
+        lib().orc_map_genome_all(self.h, lib_id, read.encode(), len(read), mode, param, seedlen, trim3, int(norc), _p(cnt))
+        return [int(x) for x in cnt]
+
+    def a2i_genome_filter(self, lib_id, reads):
+        """writeDataToCSV.py:1260-1281: `bowtie genome -n 1 -a -3 2`; a read is retained when it aligns and its
+        lowest occupied mismatch stratum holds exactly one alignment."""
+        kept = {}
+        for r in reads:
+            c = self.genome_hits(lib_id, r, 0, 1, 28, 2)
+            occupied = [x for x in c if x]
+            if occupied and occupied[0] == 1:
+                kept[r] = True
+        return kept
 
     def export(self):
         U = int(lib().orc_n_unique(self.h))
