@@ -17,6 +17,7 @@ and index paths (`file_mirna`, ...) are resolved to the `<index>.fa` next to the
 """
 import os
 
+from . import gff as gff_mod
 from . import tables
 from .engine import Engine, LIB_IDS, ROUND_LIB
 from .libs import read_fasta
@@ -118,6 +119,15 @@ def runAnnotationPipeline(bowtieBinary, seqDic, numCPU, phred64, annotNameList, 
             a = seqDic[seq.decode()]['annot']
             a[0] = 1
             a[ro] = s.engine.lib_names[ROUND_LIB[ro - 1]][int(u['ref_of'][k])]
+    if gff_output and isomiRContentDic is not None:
+        # updateIsomiRDic / updateIsomiRDic2 (runAnnotationPipeline.py:382-446): same keys, values as strings
+        mir_names, mir_seqs = read_fasta(file_mirna + '.fa')
+        hp_names, hp_seqs = read_fasta(file_hairpin + '.fa')
+        recs = gff_mod.gff_rows(u, mir_names, mir_seqs, hp_names, hp_seqs, miRNamePreNameDic or {}, miRNA_database or 'miRBase')
+        for seq, r in recs.items():
+            isomiRContentDic[seq] = {'miRName': r['miRName'], 'preMiRName': r['preMiRName'], 'type': r['type'], 'variant': r['variant'],
+                                     'pre_start': str(r['pre_start']), 'pre_end': str(r['pre_end']), 'cigar': r['cigar'], 'strand': '+',
+                                     'uid': r['uid'], 'annot': 1, 'filter': 'Pass'}
     t = s.engine.export_tables_prelim()
     for r in range(len(annotNameList)):
         logDic['annotStats'].append({'readsProcessed': int(t['round_processed'][r]), 'readsAligned': int(t['round_aligned'][r]),
