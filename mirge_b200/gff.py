@@ -194,7 +194,7 @@ def gff_rows(uniq, mirna_names, mirna_seqs, hairpin_names, hairpin_seqs, pre_of,
         d = describe_read(pre, lib_entry, read, int(uniq['pos_of'][u]) + 1, uniq['round_of'][u] == 9)
         if d is None:
             continue
-        recs[read] = dict(miRName=name, preMiRName=parent, type=d[0], variant=d[1], pre_start=d[2], pre_end=d[3], cigar=d[4],
+        recs[read] = dict(miRName=name, preMiRName=parent, start=int(uniq['pos_of'][u]) + 1, type=d[0], variant=d[1], pre_start=d[2], pre_end=d[3], cigar=d[4],
                           uid=read_uid(read), counts=[int(c) for c in uniq['counts'][u]])
     return recs
 

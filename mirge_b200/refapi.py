@@ -127,7 +127,7 @@ def runAnnotationPipeline(bowtieBinary, seqDic, numCPU, phred64, annotNameList, 
         for seq, r in recs.items():
             isomiRContentDic[seq] = {'miRName': r['miRName'], 'preMiRName': r['preMiRName'], 'type': r['type'], 'variant': r['variant'],
                                      'pre_start': str(r['pre_start']), 'pre_end': str(r['pre_end']), 'cigar': r['cigar'], 'strand': '+',
-                                     'uid': r['uid'], 'annot': 1, 'filter': 'Pass'}
+                                     'uid': r['uid'], 'start': str(r['start']), 'annot': 1, 'filter': 'Pass'}
     t = s.engine.export_tables_prelim()
     for r in range(len(annotNameList)):
         logDic['annotStats'].append({'readsProcessed': int(t['round_processed'][r]), 'readsAligned': int(t['round_aligned'][r]),
