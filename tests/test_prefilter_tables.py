@@ -13,7 +13,8 @@ from conftest import ILLUMINA
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ADAPTERS = [ILLUMINA, 'TGGAATTCTCGGGTGCCAAGG', 'AAAAAAAAAAAAAAAA', 'ACACACACACACACACACAC', 'TGGAATTC',
-            'AGATCGGAAGAGCACACGTCTGAACTCCAGTC', 'AGATCGGAAGAGC', 'TTTTGGAATTTTGGAATTGGAATT', 'GATCGATCGGATCGATCGATCG']
+            'AGATCGGAAGAGCACACGTCTGAACTCCAGTC', 'AGATCGGAAGAGC', 'TTTTGGAATTTTGGAATTGGAATT', 'GATCGATCGGATCGATCGATCG',
+            'AACTGTAGGCACCATCAAT', 'AGATCGGAAGAGCACACGTC', 'CTGTCTCTTATACACATCT', 'TCGTATGCCGTCTTCTGCTTG']   # Qiagen, NEBNext, Nextera, Illumina v1.0 small RNA
 
 
 class PfTables(C.Structure):
