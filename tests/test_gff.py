@@ -165,3 +165,22 @@ def test_missing_snpc_entry_is_reported():
     uniq = dict(seq=np.array([b'ACGTACGTACGTACGTACGT']), counts=np.array([[1]]), round_of=np.array([1]), ref_of=np.array([0]), pos_of=np.array([2]))
     with pytest.raises(gff.GffError):
         gff.gff_rows(uniq, ['x-miR-1-5p.SNP1'], ['TTACGTACGTACGTACGTACGTAAAAAA'], ['x-mir-1'], ['GGTTACGTACGTACGTACGTACGTAAAAAAGG'], {'x-miR-1-5p': 'x-mir-1'}, 'miRBase')
+
+
+def test_product_reproduces_committed_gff_fixture(tmp_path):
+    """tests/golden/gff_case.json.gz (made by make_golden_gff.py from the oracle's literal restatement)."""
+    import gzip
+    import json
+    with gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'gff_case.json.gz'), 'rt') as f:
+        case = json.load(f)
+    gff3 = tmp_path / 'x.gff3'
+    gff3.write_text(case['gff3'])
+    pre_of = gff.stem_loop_names(str(gff3), 'miRBase')
+    u = case['uniq']
+    uniq = dict(seq=np.array([r[0].encode() for r in u]), counts=np.array([r[1] for r in u], np.uint32), round_of=np.array([r[2] for r in u], np.int8),
+                ref_of=np.array([r[3] for r in u], np.int32), pos_of=np.array([r[4] for r in u], np.int32))
+    recs = gff.gff_rows(uniq, case['mirna'][0], case['mirna'][1], case['hairpin'][0], case['hairpin'][1], pre_of, 'miRBase')
+    for sample, path in zip(case['samples'], gff.write_gff(str(tmp_path), recs, case['samples'], 'miRBase')):
+        text = open(path).read()
+        assert text.startswith(case['header'][sample])
+        assert sorted(text[len(case['header'][sample]):].splitlines(True)) == case['rows'][sample]
