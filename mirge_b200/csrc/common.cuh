@@ -17,6 +17,33 @@ typedef long long i64;
 #define ERRF_TOOLONG 2u
 #define ERRF_FULL 4u
 
+// Bit helpers usable from host code too (tests/helpers/prefilter_host.cu runs the
+// prefilter's device function on the CPU); on the device they are the intrinsics.
+__host__ __device__ __forceinline__ int bit_ffs32(u32 x)
+{
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+__host__ __device__ __forceinline__ int bit_ffs64(u64 x)
+{
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)x);
+#else
+    return __builtin_ffsll((long long)x);
+#endif
+}
+__host__ __device__ __forceinline__ u32 bit_funnel_r(u32 lo, u32 hi, int sh)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (u32)(((((u64)hi) << 32) | (u64)lo) >> (sh & 31));
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // Packed sequence: base i lives in bits [2i, 2i+1] of word i/32; A=0 C=1 G=2 T=3.
 // Ambiguity mask: bit i of word i/64 set when base i is not ACGT (packed as 0).
@@ -155,7 +182,7 @@ __host__ __device__ __forceinline__ u64 spread32(u32 x)
 
 // 64-bit window (32 bases) of a W-word 2-bit array starting at base offset `so`
 template <int W>
-__device__ __forceinline__ u64 words_window64(const u64 *a, int so)
+__host__ __device__ __forceinline__ u64 words_window64(const u64 *a, int so)
 {
     const int ws = so >> 5, bs = (so & 31) * 2;
     u64 lo = 0ull, hi = 0ull;
@@ -169,7 +196,7 @@ __device__ __forceinline__ u64 words_window64(const u64 *a, int so)
 
 // 32-bit window of a 1-bit-per-base mask (NW words) starting at base offset `so`
 template <int NW>
-__device__ __forceinline__ u32 mask_window32(const u64 *a, int so)
+__host__ __device__ __forceinline__ u32 mask_window32(const u64 *a, int so)
 {
     const int ws = so >> 6, bs = so & 63;
     u64 lo = 0ull, hi = 0ull;

@@ -48,7 +48,7 @@ struct K1Pre {
 // Returns the class (0, 1, 2).  Class 0/1: rstart = start of FULL / E.  Class 1: limit =
 // last column whose full-length cost must be checked.
 template <int W>
-__device__ __forceinline__ int k1_prefilter(const PSeq<W> &p, int n, const K1Pre &pre, u64 aw, int &rstart, int &limit)
+__host__ __device__ __forceinline__ int k1_prefilter(const PSeq<W> &p, int n, const K1Pre &pre, u64 aw, int &rstart, int &limit)
 {
     constexpr int NW = 2 * W;
     u32 w[NW + 1];
@@ -63,7 +63,7 @@ __device__ __forceinline__ int k1_prefilter(const PSeq<W> &p, int n, const K1Pre
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int k = 0; k < NW; k++) {
-            const u32 y = r ? __funnelshift_r(w[k], w[k + 1], 2 * r) : w[k];
+            const u32 y = r ? bit_funnel_r(w[k], w[k + 1], 2 * r) : w[k];
             const u32 x = y ^ rep;
             const u32 z = (x - 0x01010101u) & ~x & 0x80808080u;      // zero bytes (may over-report; every hit is verified)
             c[k] |= z >> (7 - 2 * r);                                 // occurrence at base 16k + 4b + r -> bit 8b + 2r
@@ -87,7 +87,7 @@ __device__ __forceinline__ int k1_prefilter(const PSeq<W> &p, int n, const K1Pre
 #pragma unroll
         for (int k = W - 1; k >= 0; k--) if (cc[k]) { kk = k; cur = cc[k]; }
         if (kk < 0) break;
-        const int b = __ffsll((long long)cur) - 1;
+        const int b = bit_ffs64(cur) - 1;
 #pragma unroll
         for (int k = 0; k < W; k++) if (k == kk) cc[k] &= cc[k] - 1;
         const int pos = kk * 32 + (b >> 1);
@@ -95,10 +95,10 @@ __device__ __forceinline__ int k1_prefilter(const PSeq<W> &p, int n, const K1Pre
         u64 mm = (x | (x >> 1)) & 0x5555555555555555ull;
         const int vl = (n - pos) < m ? (n - pos) : m;
         if (vl < 32) mm |= 1ull << (2 * vl);
-        int ml = mm ? ((__ffsll((long long)mm) - 1) >> 1) : 32;
+        int ml = mm ? ((bit_ffs64(mm) - 1) >> 1) : 32;
         u32 nb = mask_window32<W / 2>(p.nm, pos);
         if (ml < 32) nb &= (1u << ml) - 1u;
-        if (nb) ml = __ffs(nb) - 1;
+        if (nb) ml = bit_ffs32(nb) - 1;
         if (ml >= m) { rstart = pos; return 0; }                      // FULL: leftmost, occurrences are visited in order
         if (pos + ml >= n) {                                          // E with l = ml, I = pos
             rstart = pos;

@@ -150,3 +150,13 @@ void pf_check_fastq(const PfTables *T, const char *A, const char *buf, uint64_t 
         p = l[4];
     }
 }
+
+/* Batch form of the model's classifier (for the comparison with the device function run on the host). */
+void pf_classify_batch(const PfTables *T, const char *A, const char *reads, const uint64_t *off, uint64_t n_reads, int *out)
+{
+    for (uint64_t k = 0; k < n_reads; k++) {
+        int rs = -1, lim = 0;
+        out[3 * k] = pf_classify(T, A, reads + off[k], (int)(off[k + 1] - off[k]), &rs, &lim);
+        out[3 * k + 1] = rs; out[3 * k + 2] = lim;
+    }
+}

@@ -136,3 +136,77 @@ def test_model_agrees_with_oracle_on_the_bench_workload(model, small_world):
     model.pf_check_fastq(C.byref(t), ILLUMINA.encode(), fq, C.c_uint64(len(fq)), 33, 10, C.c_double(0.12), 3, st.ctypes.data_as(C.c_void_p))
     assert int(st[5]) == 300000 and int(st[4]) == 0
     assert st[0] > 0.55 * st[5] and st[2] < 0.15 * st[5]          # most reads are settled without DP
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the DEVICE classification function, compiled for the host (tests/helpers/prefilter_host.cu), against the model
+# ---------------------------------------------------------------------------------------------------------
+class K1Pre(C.Structure):       # mirge_b200/csrc/k1_prefilter.cuh
+    _fields_ = [('enabled', C.c_int), ('m', C.c_int), ('icap', C.c_int), ('anchor_rep', C.c_uint32), ('safe_p', C.c_uint32),
+                ('safe_len', C.c_uint32 * 49), ('fullreach', C.c_uint8 * 32)]
+
+
+@pytest.fixture(scope='module')
+def host_kernel():
+    import shutil
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    so = os.path.join(HERE, 'helpers', 'libprefilter_host.so')
+    srcs = [os.path.join(HERE, 'helpers', 'prefilter_host.cu'),
+            os.path.join(HERE, '..', 'mirge_b200', 'csrc', 'k1_prefilter.cuh'), os.path.join(HERE, '..', 'mirge_b200', 'csrc', 'common.cuh')]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call([nvcc, '-O2', '-std=c++17', '-arch=sm_100a', '-shared', '-Xcompiler', '-fPIC', '-o', so, srcs[0]])
+    return C.CDLL(so)
+
+
+def _adversarial_batch(rng, adapter, n_reads, maxlen):
+    m = len(adapter)
+    reads = []
+    for _ in range(n_reads):
+        ilen = int(rng.integers(0, maxlen + 1))
+        kind = int(rng.integers(0, 4))
+        ins = []
+        while len(ins) < ilen:
+            mode = 0 if kind == 0 else int(rng.integers(0, 3))
+            if mode == 0:
+                ins.append('ACGT'[rng.integers(0, 4)])
+            elif mode == 1:
+                a = int(rng.integers(0, m)); ins.extend(adapter[a:a + int(rng.integers(1, m + 1))])
+            else:
+                ins.extend(adapter[:int(rng.integers(1, 9))])          # anchors (and near-anchors) inside the insert
+        r = (''.join(ins[:ilen]) + adapter[:int(rng.integers(0, m + 1))])[:maxlen]
+        if rng.random() < 0.2:
+            r = (r + adapter + 'ACGT'[rng.integers(0, 4)] * int(rng.integers(0, 6)))[:maxlen]
+        if rng.random() < 0.1 and r:
+            q = int(rng.integers(0, len(r))); r = r[:q] + 'N' + r[q + 1:]
+        reads.append(r)
+    return reads
+
+
+@pytest.mark.parametrize('adapter', [ILLUMINA, 'AAAAAAAAAAAAAAAA', 'ACACACACACACACACACAC', 'TGGAATTC', 'AGATCGGAAGAGCACACGTCTGAACTCCAGTC',
+                                     'AACTGTAGGCACCATCAAT'])
+@pytest.mark.parametrize('maxlen,W', [(50, 2), (64, 2), (128, 4), (70, 4)])
+def test_device_classifier_on_host_matches_model(model, host_kernel, adapter, maxlen, W):
+    on, t = product_tables(adapter)
+    assert on == 1
+    aw = sum('ACGT'.index(c) << (2 * i) for i, c in enumerate(adapter))
+    pre = K1Pre(enabled=1, m=t.m, icap=t.icap, anchor_rep=((aw & 0xFF) * 0x01010101) & 0xFFFFFFFF, safe_p=t.safe_p)
+    for i in range(49):
+        pre.safe_len[i] = t.safe_len[i]
+    for i in range(32):
+        pre.fullreach[i] = t.fullreach[i]
+    rng = np.random.default_rng(len(adapter) * 7 + maxlen + W)
+    reads = _adversarial_batch(rng, adapter, 20000, maxlen)
+    off = np.zeros(len(reads) + 1, np.uint64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    cat = ''.join(reads).encode() + b'\0'
+    got = np.zeros(3 * len(reads), np.int32)
+    want = np.zeros(3 * len(reads), np.int32)
+    host_kernel.pfh_classify_batch(C.byref(pre), C.c_uint64(aw), cat, off.ctypes.data_as(C.c_void_p), C.c_uint64(len(reads)), W, got.ctypes.data_as(C.c_void_p))
+    model.pf_classify_batch(C.byref(t), adapter.encode(), cat, off.ctypes.data_as(C.c_void_p), C.c_uint64(len(reads)), want.ctypes.data_as(C.c_void_p))
+    got, want = got.reshape(-1, 3), want.reshape(-1, 3)
+    bad = np.flatnonzero((got != want).any(axis=1))
+    assert bad.size == 0, (reads[bad[0]], got[bad[0]].tolist(), want[bad[0]].tolist())
+    seen = set(got[:, 0].tolist())
+    assert {0, 2} <= seen and (adapter != ILLUMINA or 1 in seen)
