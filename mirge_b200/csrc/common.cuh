@@ -35,6 +35,22 @@ __host__ __device__ __forceinline__ int bit_ffs64(u64 x)
     return __builtin_ffsll((long long)x);
 #endif
 }
+__host__ __device__ __forceinline__ int bit_popc32(u32 x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+__host__ __device__ __forceinline__ int bit_clz64(u64 x)     // x != 0 on the host side
+{
+#ifdef __CUDA_ARCH__
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
 __host__ __device__ __forceinline__ u32 bit_funnel_r(u32 lo, u32 hi, int sh)
 {
 #ifdef __CUDA_ARCH__
@@ -62,7 +78,7 @@ __host__ __device__ __forceinline__ int base_code(unsigned char c)
 }
 
 template <int W>
-__device__ __forceinline__ int pseq_base(const PSeq<W> &p, int j)
+__host__ __device__ __forceinline__ int pseq_base(const PSeq<W> &p, int j)
 {
     u64 w = p.s[0];
 #pragma unroll
@@ -70,7 +86,7 @@ __device__ __forceinline__ int pseq_base(const PSeq<W> &p, int j)
     return (int)((w >> ((j & 31) * 2)) & 3ull);
 }
 template <int W>
-__device__ __forceinline__ int pseq_isn(const PSeq<W> &p, int j)
+__host__ __device__ __forceinline__ int pseq_isn(const PSeq<W> &p, int j)
 {
     u64 w = p.nm[0];
 #pragma unroll

@@ -262,7 +262,7 @@ __device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimP
 // are kept (thread-local arrays), so nothing is out of reach.  Not warp-collective;
 // run by converged threads when the slow queue is drained.
 template <int W>
-__device__ int k1_match_full(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, int a,
+__host__ __device__ int k1_match_full(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, int a,
                              const u32 *peq8, int &matches_out)
 {
     const int m = tp.alen[a];
@@ -316,12 +316,12 @@ __device__ int k1_match_full(const PSeq<W> &p, int n, const TrimParams &tp, cons
             u64 f = 0;
 #pragma unroll
             for (int w = 0; w < W / 2; w++) if (fw == w) f = fullc[w];
-            const int t = __ffsll((long long)f) - 1;
+            const int t = bit_ffs64(f) - 1;
 #pragma unroll
             for (int w = 0; w < W / 2; w++) if (fw == w) fullc[w] &= fullc[w] - 1;
             i = m; j = fw * 64 + t + 1; visit = j;
         } else if (valid) {
-            i = 63 - __clzll(valid);
+            i = 63 - bit_clz64(valid);
             valid &= ~(1ull << i);
             if (i < best_m) break;
             j = n; visit = n + 1 + (m - i);
@@ -330,7 +330,7 @@ __device__ int k1_match_full(const PSeq<W> &p, int n, const TrimParams &tp, cons
         }
         const u64 vj = cv[j - 1];
         const u32 low = (i >= 32) ? 0xFFFFFFFFu : ((1u << i) - 1u);
-        const int c = __popc((u32)vj & low) - __popc((u32)(vj >> 32) & low);
+        const int c = bit_popc32((u32)vj & low) - bit_popc32((u32)(vj >> 32) & low);
         if (j == n && i == best_m && c >= best_c) continue;
         int ci = i, cj = j, cc = c, mt = 0, o = -1;
         for (;;) {
@@ -344,7 +344,7 @@ __device__ int k1_match_full(const PSeq<W> &p, int n, const TrimParams &tp, cons
                 const u64 x = words_window64<W>(p.s, d) ^ aw;
                 u64 mm = ((x | (x >> 1)) & 0x5555555555555555ull) | spread32(mask_window32<W / 2>(p.nm, d));
                 if (ci < 32) mm &= (1ull << (2 * ci)) - 1ull;
-                run = mm ? ci - 1 - ((63 - __clzll(mm)) >> 1) : ci;
+                run = mm ? ci - 1 - ((63 - bit_clz64(mm)) >> 1) : ci;
             } else if (peq8[pseq_base<W>(p, cj - 1) | (pseq_isn<W>(p, cj - 1) << 2)] & bit) {
                 run = 1;
             }

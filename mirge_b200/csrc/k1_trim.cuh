@@ -236,7 +236,7 @@ struct TrimParams {
 // (see oracle/mirge_oracle.c:orc_locate).  Column entries are packed as
 // cost | matches << 8 | origin << 16.
 template <int W>
-__device__ bool locate_back(const PSeq<W> &p, int n, const u64 *aw, int m, double rate, int min_overlap,
+__host__ __device__ bool locate_back(const PSeq<W> &p, int n, const u64 *aw, int m, double rate, int min_overlap,
                             int &rstart, int &matches_out)
 {
     u32 col[MIRGE_MAX_ADAPTER_LEN + 1];
@@ -294,7 +294,7 @@ __device__ bool locate_back(const PSeq<W> &p, int n, const u64 *aw, int m, doubl
 // Adapter.match_to (cutadapt adapters.py), where = BACK, no wildcards:
 // leftmost exact occurrence (str.find) first, else Aligner.locate.
 template <int W>
-__device__ __forceinline__ bool match_back(const PSeq<W> &p, int n, const TrimParams &tp, int a,
+__host__ __device__ __forceinline__ bool match_back(const PSeq<W> &p, int n, const TrimParams &tp, int a,
                                            int &rstart, int &matches)
 {
     const int m = tp.alen[a];

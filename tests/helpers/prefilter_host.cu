@@ -34,3 +34,57 @@ extern "C" void pfh_classify_batch(const K1Pre *pre, unsigned long long aw, cons
     for (unsigned long long k = 0; k < n_reads; k++)
         out[3 * k] = pfh_classify(pre, aw, reads + off[k], (int)(off[k + 1] - off[k]), W, out + 3 * k + 1, out + 3 * k + 2);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// The per-thread adapter searches of the slow queue, on the host: k1_match_full (all-column bit-vector search,
+// adapters <= 32 nt) and match_back (exact find + the cell-for-cell banded DP locate_back).
+// ---------------------------------------------------------------------------------------------------------
+#include "../../mirge_b200/csrc/k1_kernel.cuh"
+
+template <int W>
+static int match_one(const char *adapter, double rate, int min_overlap, const char *read, int n, int literal, int *rstart, int *matches)
+{
+    TrimParams tp;
+    memset(&tp, 0, sizeof tp);
+    tp.mode = 1; tp.n_adapters = 1; tp.error_rate = rate; tp.min_overlap = min_overlap;
+    const int m = (int)strlen(adapter);
+    tp.alen[0] = m;
+    for (int i = 0; i < m; i++) {
+        const int c = base_code((unsigned char)adapter[i]);
+        tp.aw[0][i >> 5] |= (u64)c << ((i & 31) * 2);
+        tp.peq[0][c] |= 1ull << i;
+    }
+    signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
+    for (int i = 0; i <= MIRGE_MAX_ADAPTER_LEN; i++) {
+        int c = -1;
+        if (i >= min_overlap) { c = 0; while ((double)(c + 1) <= (double)i * rate) c++; }
+        thr[i] = (signed char)c;
+    }
+    u32 peq8[8];
+    for (int k = 0; k < 8; k++) peq8[k] = (k & 4) ? 0u : (u32)tp.peq[0][k & 3];
+    PSeq<W> p;
+    for (int w = 0; w < W; w++) p.s[w] = 0;
+    for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
+    for (int i = 0; i < n; i++) {
+        int c = base_code((unsigned char)read[i]);
+        if (c > 3) { p.nm[i >> 6] |= 1ull << (i & 63); c = 0; }
+        p.s[i >> 5] |= (u64)c << ((i & 31) * 2);
+    }
+    int rs = -1, mt = 0;
+    bool found;
+    if (m <= 32 && !literal) { rs = k1_match_full<W>(p, n, tp, thr, 0, peq8, mt); found = rs >= 0; }
+    else found = match_back<W>(p, n, tp, 0, rs, mt);
+    *rstart = rs; *matches = mt;
+    return found ? 1 : 0;
+}
+
+// out[3k..3k+2] = found, rstart, matches
+extern "C" void pfh_match_batch(const char *adapter, double rate, int min_overlap, const char *reads, const unsigned long long *off,
+                                unsigned long long n_reads, int W, int literal, int *out)
+{
+    for (unsigned long long k = 0; k < n_reads; k++) {
+        const int n = (int)(off[k + 1] - off[k]);
+        out[3 * k] = W == 2 ? match_one<2>(adapter, rate, min_overlap, reads + off[k], n, literal, out + 3 * k + 1, out + 3 * k + 2)
+                            : match_one<4>(adapter, rate, min_overlap, reads + off[k], n, literal, out + 3 * k + 1, out + 3 * k + 2);
+    }
+}

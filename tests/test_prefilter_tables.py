@@ -146,20 +146,6 @@ class K1Pre(C.Structure):       # mirge_b200/csrc/k1_prefilter.cuh
                 ('safe_len', C.c_uint32 * 49), ('fullreach', C.c_uint8 * 32)]
 
 
-@pytest.fixture(scope='module')
-def host_kernel():
-    import shutil
-    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
-    if not os.path.exists(nvcc):
-        pytest.skip('nvcc not available')
-    so = os.path.join(HERE, 'helpers', 'libprefilter_host.so')
-    srcs = [os.path.join(HERE, 'helpers', 'prefilter_host.cu'),
-            os.path.join(HERE, '..', 'mirge_b200', 'csrc', 'k1_prefilter.cuh'), os.path.join(HERE, '..', 'mirge_b200', 'csrc', 'common.cuh')]
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call([nvcc, '-O2', '-std=c++17', '-arch=sm_100a', '-shared', '-Xcompiler', '-fPIC', '-o', so, srcs[0]])
-    return C.CDLL(so)
-
-
 def _adversarial_batch(rng, adapter, n_reads, maxlen):
     m = len(adapter)
     reads = []
