@@ -51,6 +51,23 @@ __host__ __device__ __forceinline__ int bit_clz64(u64 x)     // x != 0 on the ho
     return x ? __builtin_clzll(x) : 64;
 #endif
 }
+// Warp votes; on the host a "warp" is the single calling thread (the per-lane logic is what the host tests run).
+__host__ __device__ __forceinline__ int warp_max_all(int v)
+{
+#ifdef __CUDA_ARCH__
+    return __reduce_max_sync(0xffffffffu, v);
+#else
+    return v;
+#endif
+}
+__host__ __device__ __forceinline__ bool warp_any_all(bool p)
+{
+#ifdef __CUDA_ARCH__
+    return __any_sync(0xffffffffu, p) != 0;
+#else
+    return p;
+#endif
+}
 __host__ __device__ __forceinline__ u32 bit_funnel_r(u32 lo, u32 hi, int sh)
 {
 #ifdef __CUDA_ARCH__

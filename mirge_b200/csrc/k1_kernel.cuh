@@ -60,12 +60,12 @@ __device__ __forceinline__ void k1_load_record(const u64 *__restrict__ bases, co
 }
 
 // cost of DP cell (i, j) from the ring of column bit-vectors; column 0 is cost i.
-__device__ __forceinline__ int k1_cell_cost(const u64 *ring, int i, int j)
+__host__ __device__ __forceinline__ int k1_cell_cost(const u64 *ring, int i, int j)
 {
     if (j == 0) return i;
     const u64 v = ring[(j & (K1_RING - 1)) * K1_THREADS];
     const u32 low = (i >= 32) ? 0xFFFFFFFFu : ((1u << i) - 1u);
-    return __popc((u32)v & low) - __popc((u32)(v >> 32) & low);
+    return bit_popc32((u32)v & low) - bit_popc32((u32)(v >> 32) & low);
 }
 
 #define K1_NOMATCH (-1)
@@ -85,7 +85,7 @@ __device__ __forceinline__ int k1_cell_cost(const u64 *ring, int i, int j)
 // Returns rstart >= 0 (matches in matches_out), K1_NOMATCH, or K1_SLOW.
 // `ring`/`ringh` point at this thread's slot 0 (stride K1_THREADS between slots).
 template <int W>
-__device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, int a,
+__host__ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, int a,
                                              u64 *ring, u32 *ringh, const u32 *peq8, int &matches_out)
 {
     // peq8[c | isN << 2]: match mask of read base c against the adapter (0 for N)
@@ -99,7 +99,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
     u32 full_mask = 0;                             // bit (j - win_lo): inexact full-length candidate ending at column j
     bool slow = false;
     int exact_j = -1;
-    const int nmax = __reduce_max_sync(0xffffffffu, n);
+    const int nmax = warp_max_all(n);
     for (int j0 = 0; j0 < nmax; j0 += 16) {        // 16 bases (one 32-bit word) per outer step
         u32 bw = 0, nb = 0;
 #pragma unroll
@@ -136,7 +136,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
         }
         // once per 16 columns: leftmost exact occurrence (str.find), full-length candidates
         // inside the window, and inexact full-length occurrences far from the read end
-        if (z16 && exact_j < 0) exact_j = j0 + __ffs(z16);
+        if (z16 && exact_j < 0) exact_j = j0 + bit_ffs32(z16);
         if (le16) {
             int below = win_lo - 1 - j0;           // columns of this chunk that lie before the window
             below = below < 0 ? 0 : (below > 16 ? 16 : below);
@@ -160,16 +160,16 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
     // per-lane state machine: state 0 = fetch next candidate, 1 = walking back, 2 = finished
     int state = (exact_j >= 0 || slow) ? 2 : 0;
     int ci = 0, cj = 0, cc = 0, c0 = 0, mt = 0, visit = 0;
-    while (__any_sync(0xffffffffu, state != 2)) {
+    while (warp_any_all(state != 2)) {
         if (state == 0) {
             int i = 0, j = 0;
             bool have = true;
             if (full_mask) {
-                const int t = __ffs(full_mask) - 1;
+                const int t = bit_ffs32(full_mask) - 1;
                 full_mask &= full_mask - 1;
                 i = m; j = win_lo + t; visit = j;
             } else if (valid) {
-                i = 63 - __clzll(valid);
+                i = 63 - bit_clz64(valid);
                 valid &= ~(1ull << i);
                 j = n; visit = n + 1 + (m - i);
                 if (i < best_m) { have = false; state = 2; }          // matches <= i: nothing left can win
@@ -209,7 +209,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
                     const u64 x = words_window64<W>(p.s, d) ^ aw;
                     u64 mm = ((x | (x >> 1)) & 0x5555555555555555ull) | spread32(mask_window32<W / 2>(p.nm, d));
                     if (ci < 32) mm &= (1ull << (2 * ci)) - 1ull;
-                    run = mm ? ci - 1 - ((63 - __clzll(mm)) >> 1) : ci;
+                    run = mm ? ci - 1 - ((63 - bit_clz64(mm)) >> 1) : ci;
                 } else if (peq8[pseq_base<W>(p, cj - 1) | (pseq_isn<W>(p, cj - 1) << 2)] & bit) {
                     run = 1;
                 }
@@ -241,7 +241,7 @@ __device__ __forceinline__ int k1_match_fast(const PSeq<W> &p, int n, const Trim
 // AdapterCutter(times=1) over all adapters: most matches wins, first wins ties.
 // Returns the new length, or K1_SLOW.  Warp-convergent.
 template <int W>
-__device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, u64 *ring, u32 *ringh, const u32 *peq8)
+__host__ __device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, u64 *ring, u32 *ringh, const u32 *peq8)
 {
     int best_rstart = -1, best_matches = -1;
     bool slow = false;
@@ -367,7 +367,7 @@ __host__ __device__ int k1_match_full(const PSeq<W> &p, int n, const TrimParams 
 // Slow-queue reads: all-column bit-vector search per adapter (<= 32 nt), else the
 // literal banded DP (match_back -> locate_back).
 template <int W>
-__device__ __forceinline__ int k1_trim_slow(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, const u32 *peq8,
+__host__ __device__ __forceinline__ int k1_trim_slow(const PSeq<W> &p, int n, const TrimParams &tp, const signed char *thr, const u32 *peq8,
                                             bool literal)
 {
     int best_rstart = -1, best_matches = -1;

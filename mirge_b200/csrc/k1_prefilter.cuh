@@ -117,13 +117,13 @@ __host__ __device__ __forceinline__ int k1_prefilter(const PSeq<W> &p, int n, co
 // Class 1: does any column j <= limit hold a full-length candidate (cost(m, j) <= thr_m)?
 // Myers' bit-vector column recurrence, score only; warp lock-step (uniform trip count).
 template <int W>
-__device__ __forceinline__ bool k1_full_candidate_scan(const PSeq<W> &p, int limit, int m, int thr_m, const u32 *peq8)
+__host__ __device__ __forceinline__ bool k1_full_candidate_scan(const PSeq<W> &p, int limit, int m, int thr_m, const u32 *peq8)
 {
     u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
     int score = m;
     const int top = m - 1;
     bool hit = false;
-    const int lmax = __reduce_max_sync(0xffffffffu, limit);
+    const int lmax = warp_max_all(limit);
     for (int j0 = 0; j0 < lmax; j0 += 16) {
         u32 bw = 0, nb = 0;
 #pragma unroll
@@ -155,4 +155,64 @@ __device__ __forceinline__ bool k1_full_candidate_scan(const PSeq<W> &p, int lim
         hit = hit || le16 != 0u;
     }
     return hit;
+}
+
+// Class "1b" (NOT wired into the kernels yet; exercised on the host by tests/test_k1_host_compiled.py): reads that
+// end with an exact adapter prefix of l bases (l >= min_overlap) which the tables cannot settle -- typically a SHORT
+// prefix behind a long insert.  E still wins unless a candidate with more than l matches exists:
+//   * any full-length candidate (cost(m, j) <= thr[m] at some column j <= n) -> undecided (returns true);
+//   * an acceptable prefix candidate (i, n), i > l, cost c: when rows i-c+1 .. i of the last column were all reached
+//     by cutadapt's "insertion" step (bit set in the shifted negative horizontal deltas) from mismatching cells,
+//     its path runs straight up the column to the exact cell (i-c, n): matches = i - c <= l (l is the LONGEST exact
+//     prefix), so it loses to E.  Any other shape -> undecided.
+// Returns true when the general search must decide, false when rstart = n - l stands.
+template <int W>
+__host__ __device__ __forceinline__ bool k1_prefix_candidate_scan(const PSeq<W> &p, int n, int l, int m, const signed char *thr, const u32 *peq8)
+{
+    u32 Pv = (m >= 32) ? 0xFFFFFFFFu : ((1u << m) - 1u), Mv = 0;
+    int score = m;
+    const int top = m - 1, thr_m = thr[m];
+    bool hit = false;
+    u32 PvL = Pv, MvL = 0, MhL = 0, EqL = 0;          // vectors of this lane's last column
+    const int lmax = warp_max_all(n);
+    for (int j0 = 0; j0 < lmax; j0 += 16) {
+        u32 bw = 0, nb = 0;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            if ((j0 >> 5) == w) {
+                bw = (u32)(p.s[w] >> ((j0 & 16) * 2));
+                nb = (u32)(p.nm[w >> 1] >> (((w & 1) * 32) + (j0 & 16))) & 0xFFFFu;
+            }
+        }
+        const int jend = (lmax - j0) < 16 ? (lmax - j0) : 16;
+        u32 le16 = 0;
+#pragma unroll 4
+        for (int t = 0; t < jend; t++) {
+            const u32 Eq = peq8[(bw & 3u) | (((nb >> t) & 1u) << 2)];
+            bw >>= 2;
+            const u32 Xv = Eq | Mv;
+            const u32 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            u32 Ph = Mv | ~(Xh | Pv);
+            u32 Mh = Pv & Xh;
+            score += (int)((Ph >> top) & 1u) - (int)((Mh >> top) & 1u);
+            Ph <<= 1; Mh <<= 1;
+            Pv = Mh | ~(Xv | Ph);
+            Mv = Ph & Xv;
+            le16 |= (u32)(score <= thr_m) << t;
+            if (j0 + t + 1 == n) { PvL = Pv; MvL = Mv; MhL = Mh; EqL = Eq; }
+        }
+        const int keep = n - j0;
+        if (keep < 16) le16 &= keep <= 0 ? 0u : ((1u << keep) - 1u);
+        hit = hit || le16 != 0u;
+    }
+    if (hit || n < 1) return true;
+    int c = 0;
+    for (int i = 1; i < m; i++) {                      // (m, n) is a full-length cell: covered above
+        c += (int)((PvL >> (i - 1)) & 1u) - (int)((MvL >> (i - 1)) & 1u);
+        if (i <= l || c > thr[i]) continue;
+        if (c <= 0 || c >= i) return true;
+        const u32 chain = ((1u << c) - 1u) << (i - c);
+        if ((MhL & chain) != chain || (EqL & chain) != 0u) return true;
+    }
+    return false;
 }

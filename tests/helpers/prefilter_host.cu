@@ -88,3 +88,133 @@ extern "C" void pfh_match_batch(const char *adapter, double rate, int min_overla
                             : match_one<4>(adapter, rate, min_overlap, reads + off[k], n, literal, out + 3 * k + 1, out + 3 * k + 2);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// The general search (k1_trim_fast: windowed bit-vector search + candidate walks; a "warp" of one lane on the
+// host) followed, when it answers K1_SLOW, by k1_trim_slow -- the sequence k1_general_search / k1_slow_search run.
+// Adapters may be a comma-separated list.  out[2k] = trimmed length, out[2k+1] = 1 if the slow search was needed.
+// ---------------------------------------------------------------------------------------------------------
+template <int W>
+static void trim_one(const TrimParams &tp, const signed char *thr, const u32 *peq8, const char *read, int n, int *out)
+{
+    static u64 ring[K1_RING * K1_THREADS];
+    static u32 ringh[K1_RING * K1_THREADS];
+    PSeq<W> p;
+    for (int w = 0; w < W; w++) p.s[w] = 0;
+    for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
+    for (int i = 0; i < n; i++) {
+        int c = base_code((unsigned char)read[i]);
+        if (c > 3) { p.nm[i >> 6] |= 1ull << (i & 63); c = 0; }
+        p.s[i >> 5] |= (u64)c << ((i & 31) * 2);
+    }
+    int nf = k1_trim_fast<W>(p, n, tp, thr, ring, ringh, peq8);
+    out[1] = nf == K1_SLOW;
+    if (nf == K1_SLOW) nf = k1_trim_slow<W>(p, n, tp, thr, peq8, false);
+    out[0] = nf;
+}
+
+extern "C" int pfh_trim_batch(const char *spec, double rate, int min_overlap, const char *reads, const unsigned long long *off,
+                              unsigned long long n_reads, int W, int *out)
+{
+    TrimParams tp;
+    memset(&tp, 0, sizeof tp);
+    tp.mode = 1; tp.error_rate = rate; tp.min_overlap = min_overlap;
+    const char *q = spec;
+    while (*q) {
+        const char *e = strchr(q, ',');
+        const int m = e ? (int)(e - q) : (int)strlen(q);
+        if (tp.n_adapters == MIRGE_MAX_ADAPTERS || m > MIRGE_MAX_ADAPTER_LEN) return -1;
+        const int a = tp.n_adapters++;
+        tp.alen[a] = m;
+        for (int i = 0; i < m; i++) {
+            const int c = base_code((unsigned char)q[i]);
+            tp.aw[a][i >> 5] |= (u64)c << ((i & 31) * 2);
+            tp.peq[a][c] |= 1ull << i;
+        }
+        q += m;
+        if (*q == ',') q++;
+    }
+    signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
+    for (int i = 0; i <= MIRGE_MAX_ADAPTER_LEN; i++) {
+        int c = -1;
+        if (i >= min_overlap) { c = 0; while ((double)(c + 1) <= (double)i * rate) c++; }
+        thr[i] = (signed char)c;
+    }
+    u32 peq8[MIRGE_MAX_ADAPTERS * 8];
+    for (int k = 0; k < MIRGE_MAX_ADAPTERS * 8; k++) peq8[k] = (k & 4) ? 0u : (u32)tp.peq[k >> 3][k & 3];
+    for (unsigned long long k = 0; k < n_reads; k++) {
+        const int n = (int)(off[k + 1] - off[k]);
+        if (W == 2) trim_one<2>(tp, thr, peq8, reads + off[k], n, out + 2 * k);
+        else trim_one<4>(tp, thr, peq8, reads + off[k], n, out + 2 * k);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The whole per-read decision of the K1 pipeline for ONE adapter, on the host: prefilter -> class 0 / class 1 scan /
+// (optionally) the class-1b prefix scan -> general search -> slow search.  out[2k] = trimmed length,
+// out[2k+1] = path: 0 class 0, 1 class 1 settled by the scan, 2 class 1 sent on, 3 settled by the 1b scan, 4 general search.
+// ---------------------------------------------------------------------------------------------------------
+template <int W>
+static void decide_one(const K1Pre &pre, const TrimParams &tp, const signed char *thr, const u32 *peq8, const char *read, int n,
+                       int use_1b, int *out)
+{
+    static u64 ring[K1_RING * K1_THREADS];
+    static u32 ringh[K1_RING * K1_THREADS];
+    PSeq<W> p;
+    for (int w = 0; w < W; w++) p.s[w] = 0;
+    for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
+    for (int i = 0; i < n; i++) {
+        int c = base_code((unsigned char)read[i]);
+        if (c > 3) { p.nm[i >> 6] |= 1ull << (i & 63); c = 0; }
+        p.s[i >> 5] |= (u64)c << ((i & 31) * 2);
+    }
+    const int m = tp.alen[0];
+    int rs = -1, lim = 0, path = 4;
+    const int cls = pre.enabled ? k1_prefilter<W>(p, n, pre, tp.aw[0][0], rs, lim) : 2;
+    bool general = true;
+    if (cls == 0) { general = false; path = 0; }
+    else if (cls == 1) {
+        general = k1_full_candidate_scan<W>(p, lim, m, thr[m], peq8);
+        path = general ? 2 : 1;
+    } else if (use_1b && rs >= 0 && thr[n - rs] >= 0) {
+        general = k1_prefix_candidate_scan<W>(p, n, n - rs, m, thr, peq8);
+        path = general ? 4 : 3;
+    }
+    int nf = rs;
+    if (general) {
+        nf = k1_trim_fast<W>(p, n, tp, thr, ring, ringh, peq8);
+        if (nf == K1_SLOW) nf = k1_trim_slow<W>(p, n, tp, thr, peq8, false);
+    }
+    out[0] = nf; out[1] = path;
+}
+
+extern "C" int pfh_decide_batch(const K1Pre *pre, const char *adapter, double rate, int min_overlap, const char *reads,
+                                const unsigned long long *off, unsigned long long n_reads, int W, int use_1b, int *out)
+{
+    TrimParams tp;
+    memset(&tp, 0, sizeof tp);
+    tp.mode = 1; tp.n_adapters = 1; tp.error_rate = rate; tp.min_overlap = min_overlap;
+    const int m = (int)strlen(adapter);
+    if (m > MIRGE_MAX_ADAPTER_LEN) return -1;
+    tp.alen[0] = m;
+    for (int i = 0; i < m; i++) {
+        const int c = base_code((unsigned char)adapter[i]);
+        tp.aw[0][i >> 5] |= (u64)c << ((i & 31) * 2);
+        tp.peq[0][c] |= 1ull << i;
+    }
+    signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
+    for (int i = 0; i <= MIRGE_MAX_ADAPTER_LEN; i++) {
+        int c = -1;
+        if (i >= min_overlap) { c = 0; while ((double)(c + 1) <= (double)i * rate) c++; }
+        thr[i] = (signed char)c;
+    }
+    u32 peq8[MIRGE_MAX_ADAPTERS * 8];
+    for (int k = 0; k < MIRGE_MAX_ADAPTERS * 8; k++) peq8[k] = (k & 4) ? 0u : (u32)tp.peq[k >> 3][k & 3];
+    for (unsigned long long k = 0; k < n_reads; k++) {
+        const int n = (int)(off[k + 1] - off[k]);
+        if (W == 2) decide_one<2>(*pre, tp, thr, peq8, reads + off[k], n, use_1b, out + 2 * k);
+        else decide_one<4>(*pre, tp, thr, peq8, reads + off[k], n, use_1b, out + 2 * k);
+    }
+    return 0;
+}

@@ -71,3 +71,117 @@ def test_slow_queue_searches_match_oracle(host_kernel, oracle_mod, adapter, rate
                     assert got[k, 0] == 0, (adapter, reads[k], literal, got[k].tolist())
                 else:
                     assert tuple(int(x) for x in got[k]) == w, (adapter, reads[k], literal, got[k].tolist(), w)
+
+
+def _oracle_trim_len(O, adapters, read, rate, mo):
+    """AdapterCutter(times=1): most matches wins, first adapter wins ties (cutadapt modifiers.py; oracle orc_trim_read)."""
+    best = None
+    for a in adapters:
+        mb = O.match_back(a, read, rate, mo)
+        if mb and (best is None or mb[1] > best[1]):
+            best = mb
+    return best[0] if best else len(read)
+
+
+@pytest.mark.parametrize('spec', [ILLUMINA, 'TGGAATTCTCGGGTGCCAAGG', 'AAAAAAAAAAAAAAAA', 'ACACACACACACACACACAC', 'TGGAATTC',
+                                  'AGATCGGAAGAGC,TGGAATTCTCGGGTGCCAAGG', 'AGATCGGAAGAGCACACGTCTGAACTCCAGTCACATCACGATCTCGTAT'])
+@pytest.mark.parametrize('rate,mo', [(0.12, 3), (0.2, 1), (0.34, 5)])
+def test_general_search_then_slow_search_match_oracle(host_kernel, oracle_mod, spec, rate, mo):
+    """k1_trim_fast (windowed bit-vector search with candidate walks), falling back to k1_trim_slow exactly when it
+    answers K1_SLOW -- the device code of k1_general_search / k1_slow_search, one lane at a time."""
+    O = oracle_mod
+    adapters = spec.split(',')
+    rng = np.random.default_rng(len(spec) * 3 + int(rate * 100))
+    n_fast = n_slow = 0
+    for maxlen, W in ((64, 2), (120, 4)):
+        reads = _reads(rng, adapters[-1], 6000, maxlen)
+        off = np.zeros(len(reads) + 1, np.uint64)
+        off[1:] = np.cumsum([len(r) for r in reads])
+        cat = ''.join(reads).encode() + b'\0'
+        got = np.zeros(2 * len(reads), np.int32)
+        assert host_kernel.pfh_trim_batch(spec.encode(), C.c_double(rate), mo, cat, off.ctypes.data_as(C.c_void_p), C.c_uint64(len(reads)), W,
+                                          got.ctypes.data_as(C.c_void_p)) == 0
+        got = got.reshape(-1, 2)
+        for k, r in enumerate(reads):
+            assert int(got[k, 0]) == _oracle_trim_len(O, adapters, r, rate, mo), (spec, r, got[k].tolist())
+        n_slow += int(got[:, 1].sum())
+        n_fast += len(reads) - int(got[:, 1].sum())
+    if all(len(a) <= 32 for a in adapters):
+        assert n_fast > 0 and (n_slow > 0 or max(len(a) for a in adapters) <= 8)   # both outcomes of the windowed search occur
+    else:
+        assert n_fast == 0                         # adapters longer than one 32-bit word always take the slow search
+
+
+class K1Pre(C.Structure):       # mirge_b200/csrc/k1_prefilter.cuh
+    _fields_ = [('enabled', C.c_int), ('m', C.c_int), ('icap', C.c_int), ('anchor_rep', C.c_uint32), ('safe_p', C.c_uint32),
+                ('safe_len', C.c_uint32 * 49), ('fullreach', C.c_uint8 * 32)]
+
+
+def _device_tables(adapter, rate, mo):
+    from mirge_b200 import _capi
+    pre = K1Pre()
+    m, ic, sp = C.c_int(), C.c_int(), C.c_uint32()
+    pre.enabled = _capi.lib.mirge_prefilter_tables(adapter.encode(), rate, mo, C.byref(m), C.byref(ic), C.byref(sp),
+                                                   C.cast(pre.safe_len, C.c_void_p), C.cast(pre.fullreach, C.c_void_p))
+    aw = sum('ACGT'.index(c) << (2 * i) for i, c in enumerate(adapter))
+    pre.m, pre.icap, pre.safe_p, pre.anchor_rep = m.value, ic.value, sp.value, ((aw & 0xFF) * 0x01010101) & 0xFFFFFFFF
+    return pre
+
+
+def _decide(host_kernel, pre, adapter, rate, mo, reads, W, use_1b):
+    off = np.zeros(len(reads) + 1, np.uint64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    cat = ''.join(reads).encode() + b'\0'
+    got = np.zeros(2 * len(reads), np.int32)
+    assert host_kernel.pfh_decide_batch(C.byref(pre), adapter.encode(), C.c_double(rate), mo, cat, off.ctypes.data_as(C.c_void_p),
+                                        C.c_uint64(len(reads)), W, int(use_1b), got.ctypes.data_as(C.c_void_p)) == 0
+    return got.reshape(-1, 2)
+
+
+@pytest.mark.parametrize('adapter', [ILLUMINA, 'TGGAATTCTCGGGTGCCAAGG', 'ACACACACACACACACACAC', 'AGATCGGAAGAGCACACGTCTGAACTCCAGTC',
+                                     'AACTGTAGGCACCATCAAT', 'TTTTGGAATTTTGGAATTGGAATT'])
+@pytest.mark.parametrize('rate,mo', [(0.12, 3), (0.2, 1)])
+@pytest.mark.parametrize('use_1b', [False, True])
+def test_whole_read_decision_matches_oracle(host_kernel, oracle_mod, adapter, rate, mo, use_1b):
+    """prefilter -> class 0 / class-1 scan / (planned) class-1b scan -> general -> slow search: the trimmed length every
+    path of the K1 pipeline arrives at, device code on the host, against Adapter.match_to."""
+    O = oracle_mod
+    pre = _device_tables(adapter, rate, mo)
+    assert pre.enabled == 1
+    rng = np.random.default_rng(len(adapter) * 11 + int(rate * 100) + use_1b)
+    paths = set()
+    for maxlen, W in ((50, 2), (64, 2), (120, 4)):
+        reads = _reads(rng, adapter, 3000, maxlen)
+        # plus reads that END in an exact adapter prefix behind inserts of every length (the prefilter's home ground)
+        m = len(adapter)
+        for _ in range(3000):
+            ins = ''.join('ACGT'[x] for x in rng.integers(0, 4, int(rng.integers(0, maxlen))))
+            if rng.random() < 0.3:
+                ins = ins[:len(ins) // 2] + _mutate(rng, adapter, int(rng.integers(0, 4)), int(rng.integers(0, 2)), int(rng.integers(0, 2)))
+            reads.append((ins + adapter[:int(rng.integers(0, m + 1))])[:maxlen] or 'A')
+        got = _decide(host_kernel, pre, adapter, rate, mo, reads, W, use_1b)
+        for k, r in enumerate(reads):
+            mb = O.match_back(adapter, r, rate, mo)
+            assert int(got[k, 0]) == (mb[0] if mb else len(r)), (adapter, r, got[k].tolist(), mb)
+        paths.update(got[:, 1].tolist())
+    assert {0, 4} <= paths and (not use_1b or 3 in paths)
+
+
+def test_whole_read_decision_on_the_bench_workload(host_kernel, oracle_mod, small_world):
+    O = oracle_mod
+    pre = _device_tables(ILLUMINA, 0.12, 3)
+    fq = bytes(small_world.fastq(40000, seed=1000)).split(b'\n')
+    reads = []
+    for r in range(40000):
+        seq, q = fq[4 * r + 1].decode(), fq[4 * r + 3].decode()
+        st, sp = O.quality_trim_index(q, 0, 10, 33)
+        reads.append(seq[st:sp] or 'A')
+    share = {}
+    for use_1b in (False, True):
+        got = _decide(host_kernel, pre, ILLUMINA, 0.12, 3, reads, 2, use_1b)
+        for k, r in enumerate(reads):
+            mb = O.match_back(ILLUMINA, r, 0.12, 3)
+            assert int(got[k, 0]) == (mb[0] if mb else len(r)), (r, got[k].tolist(), mb)
+        share[use_1b] = np.bincount(got[:, 1], minlength=5) / float(len(reads))
+    assert share[False][0] > 0.55 and share[False][4] < 0.15          # what the kernels do today
+    assert share[True][4] < 0.07 and share[True][3] > 0.04            # the planned class 1b halves the general search's load
