@@ -132,14 +132,33 @@ def cpu_run(world, n_reads, steps, warmup, seed):
     return n_reads / sec, sec, cores
 
 
+def probe_real_reference():
+    """is the real miRge2.0 stack (python2 + cutadapt + bowtie 1.x) on this box?
+    It never is in this image; when it is, the oracle should be diffed against it first."""
+    found = {}
+    for name, cmd in (('python2+cutadapt', ['python2', '-c', 'import cutadapt; print(cutadapt.__version__)']),
+                      ('bowtie', ['bowtie', '--version']), ('bowtie-build', ['bowtie-build', '--version'])):
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=20)
+            found[name] = (r.stdout.strip().splitlines() or [''])[0][:60] if r.returncode == 0 else None
+        except Exception:
+            found[name] = None
+    return found
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    probe = probe_real_reference()
+    if all(probe.values()):
+        sys.stderr.write('bench: python2+cutadapt+bowtie found (%s) -- the real miRge2.0 could run here; this arm still '
+                         'times the oracle port (diff the oracle against the real tools first, SURVEY.md 8c)\n' % probe)
     world = build_world(args)
     sample = min(args.reads, args.cpu_sample)
     value, sec, cores = cpu_run(world, sample, args.steps, args.warmup, 1000)
-    desc = 'first %d reads of the workload per step; oracle C port (reference needs python2+cutadapt+bowtie, absent)' % sample
+    absent = ', '.join(k for k, v in probe.items() if not v) or 'none'
+    desc = 'first %d reads of the workload per step; oracle C port (real miRge2.0 needs python2+cutadapt+bowtie; probed, absent: %s)' % (sample, absent)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'reads/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

@@ -129,6 +129,12 @@ class AnnotateRun:
                 self.timers = {'quant': t2 - t0, 'annotate': time.time() - t2}
                 return self
             except MirgeError as e:
+                if e.code == -4 and self.max_read_len <= 64:
+                    # a read beyond the first 2000 records is longer than 64 nt (peek_max_read_len only samples):
+                    # rerun with the 128-nt record layout; longer reads remain the one hard limit
+                    self.max_read_len = 128
+                    self.log('a read is longer than 64 nt; retrying with max_read_len=128')
+                    continue
                 if e.code != -5 or self.max_unique >= (1 << 31):
                     raise
                 self.max_unique *= 2

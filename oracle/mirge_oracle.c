@@ -293,6 +293,7 @@ typedef struct {
 
 typedef struct {
     int n_samples, spike_in;
+    int flip_ties;          /* test knob: invert every round's (ref, pos) tie preference (orc_set_tie_policy) */
     OrcTrimCfg trim;
     OrcUniq uq;
     OrcLib *libs[ORC_MAX_LIBS];
@@ -770,6 +771,12 @@ static const OrcRound ORC_ROUNDS[10] = {
     {9,   0, 0, 0, 0, 0, 0, 0},   /* spike-in -n 0 */
 };
 
+/* Tie-policy knob: bowtie picks among equally good hits pseudo-randomly, so the
+ * count tables must not depend on WHICH of them is reported.  flip = 1 inverts the (ref, pos) preference
+ * of every round (lowest <-> highest within the fewest-mismatch stratum); tests/test_tie_policy.py runs the
+ * pipeline under both policies and checks what is and is not invariant. */
+void orc_set_tie_policy(OrcCtx *c, int flip) { c->flip_ties = flip ? 1 : 0; }
+
 /* runAnnotationPipeline.py:636-705: rounds in order over the still
  * un-annotated unique sequences (writeSeqToAnnot :543-554), updateAnnotDic
  * :341-345, poly-T special round :664-704. */
@@ -807,7 +814,7 @@ int orc_annotate(OrcCtx *c, int nthreads, uint64_t *round_processed, uint64_t *r
             }
             nproc++;
             uint64_t g; int mm;
-            if (l && map_read(l, q, n, R.mode, R.param, R.highest, &g, &mm)) {
+            if (l && map_read(l, q, n, R.mode, R.param, R.highest ^ c->flip_ties, &g, &mm)) {
                 int r = ref_of_gpos(l, g);
                 u->round_of[id] = ri + 1; u->ref_of[id] = r;
                 u->pos_of[id] = (int32_t)(g - l->off[r]); u->mm_of[id] = mm;

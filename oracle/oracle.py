@@ -50,6 +50,7 @@ def lib():
         L.orc_feed_fastq.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_int, C.c_int]
         L.orc_trim_fastq.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_reset.argtypes = [C.c_void_p]
+        L.orc_set_tie_policy.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_trim_params.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
         L.orc_n_unique.restype = C.c_uint64
         L.orc_n_unique.argtypes = [C.c_void_p]
@@ -184,6 +185,10 @@ class Oracle:
 
     def set_adapter(self, spec):
         self._check(lib().orc_set_adapter(self.h, spec.encode()))
+
+    def set_tie_policy(self, flip):
+        """Test knob: flip=True inverts every round's (ref, pos) preference among equally good hits."""
+        lib().orc_set_tie_policy(self.h, int(bool(flip)))
 
     @staticmethod
     def detect_phred(buf):
@@ -446,9 +451,12 @@ def mapped_unmapped_rows(seqDic, spikeIn):
     return mapped, unmapped
 
 
-def run_tables(o, sampleList, mirna_names, merge_lines, canoRatio='0.1'):
-    """__main__.py:375-389 after the GPU-replaceable part: summarize -> merge -> filter -> tables."""
+def run_tables(o, sampleList, mirna_names, merge_lines, canoRatio='0.1', drop=()):
+    """__main__.py:375-389 after the GPU-replaceable part: summarize -> merge -> filter -> tables.
+    drop: sequences left out of the tables (tests/test_tie_policy.py isolates the tie-dependent reads with it)."""
     seqDic = o.seqDic()
+    for s in drop:
+        del seqDic[s]
     proc, kept = o.stats()
     logDic = {'quantStats': [{'filename': s, 'totalReads': int(proc[i]), 'trimmedReads': int(kept[i])}
                              for i, s in enumerate(sampleList)], 'annotStats': []}

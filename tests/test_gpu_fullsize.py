@@ -1,7 +1,8 @@
 """GPU: BASELINE configs at their own sizes.
 C1 (1M reads, human-scale synthetic libraries): bit-exact tables against the CPU oracle.
-C2 (25M reads, one B200): size-independent properties -- count conservation, a checksum of
-checksums that is independent of chunking, and doubling under a second feed."""
+C2 (25M reads, one B200): bit-exact against the CPU oracle on the same 25 M reads (unique set, counts, round /
+reference / offset / mismatches per sequence, tallies, CSV tables), plus size-independent properties -- count
+conservation, a checksum of checksums that is independent of chunking, and doubling under a second feed."""
 import numpy as np
 import pytest
 
@@ -66,7 +67,42 @@ def _checksum(u):
     return int(np.bitwise_xor.reduce(h)), int(h.sum(dtype=np.uint64))
 
 
-def test_config_c2_properties_at_25m_reads(full_world):
+def _assert_equals_oracle(O, world, fq_bytes, e, u, t, p, k):
+    """The CUDA path's exports against the oracle run on the same reads, sequence by sequence."""
+    from mirge_b200 import tables as T
+    o = O.Oracle(1, False, ILLUMINA)
+    for tn, i in O.LIB_IDS.items():
+        o.load_library(i, *world.libs[tn])
+    o.feed_fastq(0, fq_bytes, 33)
+    o.annotate()
+    oe = o.export()
+    op, ok = o.stats()
+    assert (int(p[0]), int(k[0])) == (int(op[0]), int(ok[0]))
+    oseq = np.array([s.encode() for s in oe['seqs']], dtype=u['seq'].dtype)
+    assert len(oseq) == len(u['seq'])
+    io, ig = np.argsort(oseq, kind='stable'), np.argsort(u['seq'], kind='stable')
+    assert np.array_equal(oseq[io], u['seq'][ig])                              # the same unique set
+    assert np.array_equal(oe['counts'][io], u['counts'][ig])
+    oro, gro = oe['round_of'][io], u['round_of'][ig].astype(np.int32)
+    assert np.array_equal(oro, gro)
+    hit = oro > 0
+    for key in ('ref_of', 'pos_of', 'mm_of'):
+        assert np.array_equal(oe[key][io][hit], u[key][ig].astype(np.int32)[hit]), key
+    q, isc, tot = o.tally()
+    assert np.array_equal(t['mir_quant'], q) and np.array_equal(t['mir_iscan'], isc) and np.array_equal(t['lib_totals'], tot)
+    assert np.array_equal(t['len_hist'][:, 0], o.len_hist(len(t['len_hist']) - 1)[:, 0])
+    names = world.libs['mirna'][0]
+    want = O.run_tables(o, ['s1.fastq'], names, world.merges)
+    log = T.build_logdic(['s1.fastq'], p, k, t['lib_totals'], False)
+    mir = T.build_mirdic(names, t['mir_quant'], t['mir_iscan'])
+    T.merge_mirnas(mir, world.merges, 1)
+    T.filter_mirnas(mir, ['s1.fastq'], log, '0.1')
+    assert T.annotation_report(['s1.fastq'], log, False) == want['report']
+    assert T.mir_counts_csv(['s1.fastq'], log, mir) == want['counts']
+    assert T.mir_rpm_csv(['s1.fastq'], log, mir) == want['rpm']
+
+
+def test_config_c2_properties_at_25m_reads(full_world, oracle_mod):
     import torch
     n = 25_000_000
     rec = full_world.record_bytes(50)
@@ -89,6 +125,7 @@ def test_config_c2_properties_at_25m_reads(full_world):
     assert int(u['counts'][(u['round_of'] == 1) | (u['round_of'] == 9)].sum()) == int(tot[1])
     assert len(set(u['seq'].tolist())) == U                             # no duplicate keys in the table
     assert (u['len'] >= 16).all() and int(u['len'].max()) <= 50
+    _assert_equals_oracle(oracle_mod, full_world, host.numpy().tobytes(), e, u, t, p, k)   # bit-exact at full size
     c1 = _checksum(u)
     # same reads fed as two device-resident halves: identical table (chunking independence)
     e.reset()
