@@ -21,14 +21,15 @@
 #include "k3_tally.cuh"
 
 enum KernelId {
-    KID_K0_COUNT = 0, KID_K0_SCAN, KID_K0_LINES, KID_K0_PACK, KID_K1_TRIM, KID_K3_KEYS, KID_K3_SORT,
+    KID_K0_COUNT = 0, KID_K0_SCAN, KID_K0_LINES,          // 0..2: retired (round 1's three-pass K0)
+    KID_K0_PACK, KID_K1_TRIM, KID_K3_KEYS, KID_K3_SORT,
     KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_RESET,
     KID_K2_ROUND0 = 16,   // .. KID_K2_ROUND0 + 9
     KID_K1_CLASSIFY = 26, KID_K1_SCAN, KID_K1_GENERAL, KID_K1_SLOW,
     KID_N = 30
 };
 static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
-    "k0_count_newlines", "k0_scan", "k0_line_starts", "k0_pack", "k1_trim_collapse", "k3_make_keys",
+    "", "", "", "k0_parse_pack", "k1_trim_collapse", "k3_make_keys",
     "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "reset_memset", "", "",
     "k2_round0_mirna_exact", "k2_round1_hairpin", "k2_round2_mature_trna", "k2_round3_pre_trna", "k2_round4_snorna",
     "k2_round5_rrna", "k2_round6_ncrna_others", "k2_round7_mrna", "k2_round8_isomir", "k2_round9_spikein",
@@ -53,7 +54,7 @@ struct mirge_ctx {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;             // H2D copies of mirge_feed_fastq
     std::vector<cudaEvent_t> copy_events;
-    u32 *d_carry = nullptr;                         // line starts carried across feed regions
+    int max_warps = 148 * 64;                       // resident warps of the device (pads the warp-chunked queues)
     std::string err;
     // trim configuration
     TrimParams tp;
@@ -63,9 +64,8 @@ struct mirge_ctx {
     int force_slow = 0;
     // K0 scratch
     unsigned char *d_text = nullptr; size_t text_cap = 0;
-    u32 *d_tile = nullptr; size_t tile_cap = 0;
-    u32 *d_scan = nullptr; size_t scan_cap = 0;
-    u32 *d_lines = nullptr; size_t lines_cap = 0;
+    u64 *d_k0ctl = nullptr; size_t k0ctl_cap = 0;   // tile ticket + tile statuses of the running K0 launch
+    K0State *d_k0state = nullptr;
     u64 *d_bases = nullptr, *d_nmask = nullptr; u32 *d_meta = nullptr; size_t rec_cap = 0;
     u64 *d_q1 = nullptr; u32 *d_q2 = nullptr, *d_q3 = nullptr; u64 *d_qn = nullptr, *d_part = nullptr;   // K1 class queues (rec_cap entries each), their fills; exchange partition counters
     // unique table
@@ -73,10 +73,10 @@ struct mirge_ctx {
     u64 max_unique = 0;
     u64 *d_useq = nullptr, *d_unmask = nullptr; u8 *d_ulen = nullptr; u32 *d_counts = nullptr;
     signed char *d_round_of = nullptr, *d_mm_of = nullptr; int *d_ref_of = nullptr, *d_pos_of = nullptr;
-    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept, [2+S..5+S) K1 diagnostics (all-column search, class 1, class 2)
+    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept, [2+S..5+S) K1 diagnostics (all-column search, class 1, class 2),
+    // [5+S..5+2S) processed
     u64 *d_ctr = nullptr;
     u64 *d_len_hist = nullptr;
-    std::vector<u64> processed;
     // mapping
     DevLib libs[MIRGE_N_LIBS];
     u32 *d_todo[2] = {nullptr, nullptr};
@@ -248,7 +248,12 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     ctx->W = max_read_len <= 64 ? 2 : 4;
     ctx->max_len = ctx->W * 32;
     ctx->max_unique = max_unique;
-    ctx->processed.assign(n_samples, 0);
+    {
+        int sms = 148, tps = 2048;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaDeviceGetAttribute(&tps, cudaDevAttrMaxThreadsPerMultiProcessor, device);
+        if (sms > 0 && tps > 0) ctx->max_warps = sms * (tps / 32);
+    }
     memset(&ctx->tp, 0, sizeof ctx->tp);
     memset(&ctx->pre, 0, sizeof ctx->pre);
     ctx->tp.mode = 0; ctx->tp.error_rate = 0.12; ctx->tp.min_overlap = 3; ctx->tp.min_length = 16;
@@ -269,19 +274,19 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_mm_of, max_unique));
     CK(cudaMalloc(&ctx->d_ref_of, max_unique * sizeof(int)));
     CK(cudaMalloc(&ctx->d_pos_of, max_unique * sizeof(int)));
-    CK(cudaMalloc(&ctx->d_ctr, (5 + (size_t)n_samples) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_ctr, (5 + 2 * (size_t)n_samples) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_len_hist, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64)));
     // to-do lists: every unique once, plus the partly used chunk of every appending warp
-    CK(cudaMalloc(&ctx->d_todo[0], (max_unique + (size_t)WARPQ_CHUNK * 148 * 64) * sizeof(u32)));
-    CK(cudaMalloc(&ctx->d_todo[1], (max_unique + (size_t)WARPQ_CHUNK * 148 * 64) * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo[0], (max_unique + (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo[1], (max_unique + (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 1) * sizeof(u64)));
-    CK(cudaMalloc(&ctx->d_carry, 16 * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_k0state, sizeof(K0State)));
     CK(cudaMalloc(&ctx->d_qn, 4 * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_round_stats, 2 * MIRGE_N_ROUNDS * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_lib_totals, (size_t)n_samples * MIRGE_N_TOTALS * sizeof(i64)));
     CK(cudaMemsetAsync(ctx->d_slots, 0, cap * esz, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counts, 0, max_unique * (size_t)n_samples * sizeof(u32), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_ctr, 0, (5 + (size_t)n_samples) * sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (5 + 2 * (size_t)n_samples) * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -302,7 +307,7 @@ void mirge_destroy(mirge_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (int i = 0; i < MIRGE_N_LIBS; i++) free_lib(ctx->libs[i]);
-    cudaFree(ctx->d_text); cudaFree(ctx->d_tile); cudaFree(ctx->d_scan); cudaFree(ctx->d_lines);
+    cudaFree(ctx->d_text); cudaFree(ctx->d_k0ctl); cudaFree(ctx->d_k0state);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
     cudaFree(ctx->d_q1); cudaFree(ctx->d_q2); cudaFree(ctx->d_q3); cudaFree(ctx->d_qn); cudaFree(ctx->d_part);
     cudaFree(ctx->d_slots); cudaFree(ctx->d_useq); cudaFree(ctx->d_unmask); cudaFree(ctx->d_ulen); cudaFree(ctx->d_counts);
@@ -312,7 +317,6 @@ void mirge_destroy(mirge_ctx *ctx)
     cudaFree(ctx->d_mir_quant); cudaFree(ctx->d_mir_iscan); cudaFree(ctx->d_lib_totals); cudaFree(ctx->d_tally);
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-    cudaFree(ctx->d_carry);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -334,6 +338,7 @@ int mirge_sync(mirge_ctx *ctx)
     u64 flags = 0;
     CK(cudaMemcpy(&flags, ctx->d_ctr + 1, sizeof(u64), cudaMemcpyDeviceToHost));
     const u32 f = (u32)flags;
+    if (f & ERRF_PARTIAL) return fail(ctx, MIRGE_E_FORMAT, "FASTQ chunk does not hold a whole number of 4-line records");
     if (f & ERRF_FORMAT) return fail(ctx, MIRGE_E_FORMAT, "FASTQ format error: record does not start with '@'/'+' or sequence and quality lengths differ");
     if (f & ERRF_TOOLONG) return fail(ctx, MIRGE_E_TOOLONG, "a read is longer than max_read_len");
     if (f & ERRF_FULL) return fail(ctx, MIRGE_E_FULL, "unique-sequence table full: raise max_unique");
@@ -392,22 +397,21 @@ int mirge_detect_phred(const char *buf, uint64_t n)
     return 33;
 }
 
-__global__ void k_set_u32(u32 *p, u32 v) { *p = v; }
+#define FEED_REGION_HOST (64ull << 20)      // H2D copy granularity: kernels of region r overlap the copy of region r+1
+#define FEED_REGION_DEVICE (256ull << 20)   // text already resident: fewer, larger launches
 
-#define FEED_REGION_BYTES (64ull << 20)
-
-// Core of mirge_feed_fastq{,_device}: the chunk is consumed region by region.
-// With a host source every region's H2D copy is queued up front on the copy
-// stream, and K0/K1 of region r run on the compute stream as soon as copy r has
-// landed, so transfers overlap the kernels.  Line starts are carried across
-// regions (a record may straddle a boundary): d_lines = [q pending complete
-// lines + current partial line | line starts found in this region].
+// Core of mirge_feed_fastq{,_device}: the chunk is consumed region by region, without any host
+// synchronisation.  With a host source every region's H2D copy is queued up front on the copy
+// stream, and K0/K1 of region r run on the compute stream as soon as copy r has landed, so
+// transfers overlap the kernels.  A record may straddle a region boundary: K0 reaches back into
+// the earlier bytes of the chunk (they are resident) and the line count is carried from launch to
+// launch on the device (K0State), as is the number of records K1 has to process.
 template <int W>
 static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint64_t nbytes, int phred_base,
                         const char *host_src, int last_char)
 {
     cudaStream_t st = ctx->stream;
-    const u64 region = host_src ? FEED_REGION_BYTES : nbytes;
+    const u64 region = host_src ? FEED_REGION_HOST : FEED_REGION_DEVICE;
     const int nreg = (int)((nbytes + region - 1) / region);
     if (host_src) {
         if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -430,85 +434,58 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
     }
     K0Params kp; kp.phred_base = phred_base; kp.qual_cutoff = ctx->qual_cutoff; kp.max_len = ctx->max_len;
     K1Counters kc; kc.kept = ctx->d_ctr + 2; kc.len_hist = ctx->d_len_hist; kc.slow_reads = ctx->d_ctr + 2 + ctx->S;
-    CK(ensure(&ctx->d_lines, &ctx->lines_cap, 64));
-    CK(cudaMemsetAsync(ctx->d_lines, 0, sizeof(u32), st));       // the first line starts at offset 0
-    u32 q = 0;                                                   // complete lines pending since the last record boundary
+    // record buffers: a 4-line record is at least 6 bytes long
+    const u64 max_region = nbytes < region ? nbytes : region;
+    const u64 need_rec = max_region / 6 + 64;
+    if (need_rec > ctx->rec_cap) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
+        cudaFree(ctx->d_q1); cudaFree(ctx->d_q2); cudaFree(ctx->d_q3);
+        ctx->d_bases = ctx->d_nmask = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
+        ctx->d_q1 = nullptr; ctx->d_q2 = ctx->d_q3 = nullptr;
+        const size_t cap = need_rec + need_rec / 8;
+        CK(cudaMalloc(&ctx->d_bases, cap * W * sizeof(u64)));
+        CK(cudaMalloc(&ctx->d_nmask, cap * (W / 2) * sizeof(u64)));
+        CK(cudaMalloc(&ctx->d_meta, cap * sizeof(u32)));
+        // queues: every record once, plus the partly used chunk of every warp that appends
+        const size_t qcap = cap + (size_t)WARPQ_CHUNK * 3 * ctx->max_warps;
+        CK(cudaMalloc(&ctx->d_q1, qcap * sizeof(u64)));
+        CK(cudaMalloc(&ctx->d_q2, qcap * sizeof(u32)));
+        CK(cudaMalloc(&ctx->d_q3, qcap * sizeof(u32)));
+        ctx->rec_cap = cap;
+    }
+    const u64 max_tiles = (max_region + 1 + K0_TILE - 1) / K0_TILE;
+    CK(ensure(&ctx->d_k0ctl, &ctx->k0ctl_cap, max_tiles + 2));
+    CK(cudaMemsetAsync(ctx->d_k0state, 0, sizeof(K0State), st));      // the chunk starts at line 0
+    const int k0_grid = wave_grid(k0_parse_pack<W>, K0_THREADS, ~0ull);
     for (int r = 0; r < nreg; r++) {
         const u64 a = (u64)r * region, len = (a + region <= nbytes) ? region : nbytes - a;
         if (host_src) CK(cudaStreamWaitEvent(st, ctx->copy_events[r], 0));
-        const u64 ntiles = (len + K0_TILE_BYTES - 1) / K0_TILE_BYTES;
-        CK(ensure(&ctx->d_tile, &ctx->tile_cap, ntiles + 2));
-        CK(ensure(&ctx->d_scan, &ctx->scan_cap, scan_scratch_elems(ntiles + 1)));
-        const uint4 *t16 = reinterpret_cast<const uint4 *>(d_text + a);
-        { ProfScope ps(ctx, KID_K0_COUNT);
-          CK(cudaMemsetAsync(ctx->d_tile + ntiles, 0, sizeof(u32), st));
-          k0_count_newlines<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, len, ctx->d_tile); }
-        { ProfScope ps(ctx, KID_K0_SCAN, 0);
-          ctx->n_launches += device_excl_scan(ctx->d_tile, ctx->d_tile, ntiles + 1, ctx->d_scan, st); }
-        u32 c = 0;
-        CK(cudaMemcpyAsync(&c, ctx->d_tile + ntiles, sizeof(u32), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
         const bool last = r == nreg - 1;
-        const u32 extra = (last && last_char != '\n') ? 1u : 0u;  // unterminated final line
-        const u64 lines = (u64)q + c + extra;
-        if (last && lines % 4 != 0) return fail(ctx, MIRGE_E_FORMAT, "FASTQ chunk does not hold a whole number of 4-line records");
-        const u64 nrec = lines / 4;
-        if (ctx->lines_cap < lines + 8) {                         // grow, keeping the carried line starts
-            u32 *nl = nullptr;
-            const size_t cap = lines + lines / 8 + 64;
-            CK(cudaMalloc(&nl, cap * sizeof(u32)));
-            CK(cudaMemcpyAsync(nl, ctx->d_lines, (size_t)(q + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-            CK(cudaStreamSynchronize(st));
-            cudaFree(ctx->d_lines);
-            ctx->d_lines = nl; ctx->lines_cap = cap;
-        }
-        { ProfScope ps(ctx, KID_K0_LINES);
-          k0_line_starts<<<(unsigned)ntiles, K0_THREADS, 0, st>>>(t16, len, ctx->d_tile, ctx->d_lines, q + 1, a);
-          if (extra) { k_set_u32<<<1, 1, 0, st>>>(ctx->d_lines + q + 1 + c, (u32)(nbytes + 1)); ctx->n_launches++; } }
-        if (nrec) {
-            if (nrec > ctx->rec_cap) {
-                cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
-                cudaFree(ctx->d_q1); cudaFree(ctx->d_q2); cudaFree(ctx->d_q3);
-                ctx->d_bases = ctx->d_nmask = nullptr; ctx->d_meta = nullptr; ctx->rec_cap = 0;
-                ctx->d_q1 = nullptr; ctx->d_q2 = ctx->d_q3 = nullptr;
-                const size_t cap = nrec + nrec / 8 + 64;
-                CK(cudaMalloc(&ctx->d_bases, cap * W * sizeof(u64)));
-                CK(cudaMalloc(&ctx->d_nmask, cap * (W / 2) * sizeof(u64)));
-                CK(cudaMalloc(&ctx->d_meta, cap * sizeof(u32)));
-                // queues: every record once, plus the partly used chunk of every warp that appends
-                const size_t qcap = cap + (size_t)WARPQ_CHUNK * 3 * 148 * 64;
-                CK(cudaMalloc(&ctx->d_q1, qcap * sizeof(u64)));
-                CK(cudaMalloc(&ctx->d_q2, qcap * sizeof(u32)));
-                CK(cudaMalloc(&ctx->d_q3, qcap * sizeof(u32)));
-                ctx->rec_cap = cap;
-            }
-            { ProfScope ps(ctx, KID_K0_PACK);
-              k0_pack<W><<<grid_for(nrec, 256, 148 * 16), 256, 0, st>>>(d_text, ctx->d_lines, nrec, kp, ctx->d_bases, ctx->d_nmask,
-                                                                       ctx->d_meta, (u32 *)(ctx->d_ctr + 1)); }
-            { ProfScope ps(ctx, KID_K1_TRIM, 4);
-              K1Queues Q; Q.n = ctx->d_qn; Q.q1 = ctx->d_q1; Q.q2 = ctx->d_q2; Q.q3 = ctx->d_q3;
-              const TableView<W> T = table_view<W>(ctx);
-              CK(cudaMemsetAsync(ctx->d_qn, 0, 3 * sizeof(u64), st));
-              { ProfScope p1(ctx, KID_K1_CLASSIFY, 0);
-                k1_trim_collapse<W><<<wave_grid(k1_trim_collapse<W>, K1A_THREADS, nrec), K1A_THREADS, 0, st>>>(
-                    ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->pre, T, kc, Q, ctx->force_slow); }
-              // the queue fills live on the device: fixed grids, grid-stride loops bounded by the fill
-              { ProfScope p1(ctx, KID_K1_SCAN, 0);
-                k1_scan_class1<W><<<wave_grid(k1_scan_class1<W>, K1_THREADS, nrec), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
-              { ProfScope p1(ctx, KID_K1_GENERAL, 0);
-                k1_general_search<W><<<wave_grid(k1_general_search<W>, K1_THREADS, nrec), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
-              { ProfScope p1(ctx, KID_K1_SLOW, 0);
-                k1_slow_search<W><<<wave_grid(k1_slow_search<W>, K1_THREADS, nrec), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q,
-                                                                (ctx->force_slow & 2) ? 1 : 0); } }
-        }
-        // carry the pending line starts to the front for the next region
-        const u32 q2 = (u32)(lines % 4);
-        if (!last && nrec) {
-            CK(cudaMemcpyAsync(ctx->d_carry, ctx->d_lines + 4 * nrec, (size_t)(q2 + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-            CK(cudaMemcpyAsync(ctx->d_lines, ctx->d_carry, (size_t)(q2 + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st));
-        }
-        q = q2;
-        ctx->processed[sample] += nrec;
+        const int vnl = (last && last_char != '\n') ? 1 : 0;       // unterminated final line
+        const u32 ntiles = (u32)((len + vnl + K0_TILE - 1) / K0_TILE);
+        { ProfScope ps(ctx, KID_K0_PACK);
+          CK(cudaMemsetAsync(ctx->d_k0ctl, 0, ((size_t)ntiles + 1) * sizeof(u64), st));
+          k0_parse_pack<W><<<grid_for((u64)ntiles * K0_THREADS, K0_THREADS, k0_grid), K0_THREADS, 0, st>>>(
+              d_text, a, a + len, vnl, last ? 1 : 0, ntiles, ctx->d_k0ctl, ctx->d_k0state, r & 1, kp, ctx->rec_cap,
+              ctx->d_bases, ctx->d_nmask, ctx->d_meta, (u32 *)(ctx->d_ctr + 1), ctx->d_ctr + 5 + ctx->S + sample); }
+        const u64 *nrec = &ctx->d_k0state->nrec;
+        const u64 rec_bound = len / 6 + 1;                          // sizes the grids only
+        { ProfScope ps(ctx, KID_K1_TRIM, 4);
+          K1Queues Q; Q.n = ctx->d_qn; Q.q1 = ctx->d_q1; Q.q2 = ctx->d_q2; Q.q3 = ctx->d_q3;
+          const TableView<W> T = table_view<W>(ctx);
+          CK(cudaMemsetAsync(ctx->d_qn, 0, 3 * sizeof(u64), st));
+          { ProfScope p1(ctx, KID_K1_CLASSIFY, 0);
+            k1_trim_collapse<W><<<wave_grid(k1_trim_collapse<W>, K1A_THREADS, rec_bound), K1A_THREADS, 0, st>>>(
+                ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->pre, T, kc, Q, ctx->force_slow); }
+          // the queue fills live on the device: fixed grids, grid-stride loops bounded by the fill
+          { ProfScope p1(ctx, KID_K1_SCAN, 0);
+            k1_scan_class1<W><<<wave_grid(k1_scan_class1<W>, K1_THREADS, rec_bound), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
+          { ProfScope p1(ctx, KID_K1_GENERAL, 0);
+            k1_general_search<W><<<wave_grid(k1_general_search<W>, K1_THREADS, rec_bound), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q); }
+          { ProfScope p1(ctx, KID_K1_SLOW, 0);
+            k1_slow_search<W><<<wave_grid(k1_slow_search<W>, K1_THREADS, rec_bound), K1_THREADS, 0, st>>>(ctx->d_bases, ctx->d_nmask, ctx->d_meta, sample, ctx->tp, ctx->thr, T, kc, Q,
+                                                            (ctx->force_slow & 2) ? 1 : 0); } }
     }
     CK(cudaGetLastError());
     ctx->annotated = false; ctx->tallied = false;
@@ -546,11 +523,11 @@ int mirge_get_stats(mirge_ctx *ctx, uint64_t *processed, uint64_t *kept, uint64_
 {
     int rc = mirge_sync(ctx);
     if (rc) return rc;
-    std::vector<u64> h(2 + ctx->S);
+    std::vector<u64> h(5 + 2 * ctx->S);
     CK(cudaMemcpy(h.data(), ctx->d_ctr, h.size() * sizeof(u64), cudaMemcpyDeviceToHost));
     if (n_unique) *n_unique = h[0] < ctx->max_unique ? h[0] : ctx->max_unique;
     for (int s = 0; s < ctx->S; s++) {
-        if (processed) processed[s] = ctx->processed[s];
+        if (processed) processed[s] = h[5 + ctx->S + s];
         if (kept) kept[s] = h[2 + s];
     }
     return MIRGE_OK;
@@ -880,10 +857,9 @@ int mirge_reset(mirge_ctx *ctx)
     int rc = mirge_reset_unique(ctx);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_ctr, 0, (5 + (size_t)ctx->S) * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (5 + 2 * (size_t)ctx->S) * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * ctx->S * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), st));
-    ctx->processed.assign(ctx->S, 0);
     return MIRGE_OK;
 }
 

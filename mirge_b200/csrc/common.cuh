@@ -16,6 +16,7 @@ typedef long long i64;
 #define ERRF_FORMAT 1u
 #define ERRF_TOOLONG 2u
 #define ERRF_FULL 4u
+#define ERRF_PARTIAL 8u     // the chunk does not end on a record boundary
 
 // Bit helpers usable from host code too (tests/helpers/prefilter_host.cu runs the
 // prefilter's device function on the CPU); on the device they are the intrinsics.

@@ -1,4 +1,4 @@
-// k0_parse.cuh -- FASTQ text in HBM -> packed 2-bit read records (K0).
+// k0_parse.cuh -- FASTQ text in HBM -> packed 2-bit read records (K0), ONE pass over the text.
 //
 // Replaces the reader half of trim_file (utils/trim_file.py:102, cutadapt
 // seqio.FastqReader) and cutadapt's QualityTrimmer index computation
@@ -6,74 +6,34 @@
 // string is consumed here, once, and only the (start, stop) trim window
 // travels on to K1.
 //
-//   k0_count_newlines : per-tile newline counts (128-bit loads, SIMD byte compare)
-//   scan (scan.cuh)   : exclusive scan of tile counts
-//   k0_line_starts    : byte offset of every line start
-//   k0_pack           : one thread per 4-line record -> bases / nmask / meta
+// k0_parse_pack: a persistent grid takes 16 KiB tiles of the text in order (atomic ticket).  Per tile:
+//   1. coalesced 128-bit loads bring the tile plus a 1 KiB halo (the bytes before it) into shared
+//      memory; the '\n' mask of every 16-byte unit is computed on the way (SIMD byte compare);
+//   2. one block scan ranks the tile's newlines; their global rank -- which decides whether a line is
+//      a header, a sequence, a '+' or a quality line -- comes from a chained scan over the tiles with
+//      warp-wide decoupled look-back (status word = flag | count, one 64-bit store), seeded with the
+//      line count carried over from the previous launch (regions of one chunk are separate launches);
+//   3. every newline drops the start offset of the following line into a shared-memory list; the halo
+//      contributes its last four;
+//   4. one thread per record whose quality line ENDS in the tile packs it straight out of shared
+//      memory: aligned 32-bit loads realigned by funnel shift, four bases per step (2-bit codes and
+//      non-ACGT flags computed on all four bytes at once), quality_trim_index on both ends, format
+//      checks -> bases / nmask / meta, coalesced.
+// Records longer than the halo (kilobyte headers) take a byte-wise path through global memory; tiles
+// with more newlines than the list holds (reads of a few bases) are processed in several passes.
 #pragma once
 #include "common.cuh"
 
-#define K0_THREADS 256
-#define K0_STEPS 16                                  // 16-byte units per thread per tile
-#define K0_TILE_BYTES (K0_THREADS * 16 * K0_STEPS)   // 64 KiB
+#define K0_THREADS 128
+#define K0_TILE 16384
+#define K0_HALO 1024
+#define K0_UNITS ((K0_TILE + K0_HALO) / 16)
+#define K0_CAP 2048                 // line-start list entries per pass
+#define K0_NONE 0xFFFFu             // list entry: the line starts before the halo
 
-// 16-bit mask of '\n' bytes in the 16-byte unit `u` of the text; bytes at or
-// beyond nbytes never match.
-__device__ __forceinline__ u32 nl_mask16(const uint4 *text16, u64 u, u64 nbytes)
-{
-    u64 byte0 = u * 16ull;
-    if (byte0 >= nbytes) return 0;
-    uint4 v = __ldg(text16 + u);
-    u32 m = 0;
-    u32 w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        u32 eq = __vcmpeq4(w[k], 0x0A0A0A0Au);              // 0xFF per matching byte
-        u32 bits = ((eq & 0x01010101u) * 0x01020408u) >> 24;  // gather 4 flag bits
-        m |= (bits & 0xFu) << (4 * k);
-    }
-    u64 rem = nbytes - byte0;
-    if (rem < 16) m &= (1u << rem) - 1u;
-    return m;
-}
-
-__global__ void __launch_bounds__(K0_THREADS)
-k0_count_newlines(const uint4 *__restrict__ text16, u64 nbytes, u32 *__restrict__ tile_counts)
-{
-    __shared__ u32 sh[33];
-    u64 unit0 = (u64)blockIdx.x * (K0_THREADS * K0_STEPS);
-    u32 c = 0;
-#pragma unroll 4
-    for (int s = 0; s < K0_STEPS; s++) c += __popc(nl_mask16(text16, unit0 + (u64)s * K0_THREADS + threadIdx.x, nbytes));
-    u32 total;
-    block_excl_scan(c, sh, &total);
-    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
-}
-
-// tile_offsets = exclusive scan of tile_counts.  The k-th newline of this region
-// (0-based) puts the start of the following line into line_start[idx_base + k];
-// offsets are relative to the whole chunk (byte_base = offset of this region).
-__global__ void __launch_bounds__(K0_THREADS)
-k0_line_starts(const uint4 *__restrict__ text16, u64 nbytes, const u32 *__restrict__ tile_offsets,
-               u32 *__restrict__ line_start, u32 idx_base, u64 byte_base)
-{
-    __shared__ u32 sh[33];
-    u64 unit0 = (u64)blockIdx.x * (K0_THREADS * K0_STEPS);
-    u32 base = tile_offsets[blockIdx.x] + idx_base;
-    for (int s = 0; s < K0_STEPS; s++) {
-        u64 u = unit0 + (u64)s * K0_THREADS + threadIdx.x;
-        u32 m = nl_mask16(text16, u, nbytes);
-        u32 total;
-        u32 pre = block_excl_scan(__popc(m), sh, &total);
-        u32 idx = base + pre;
-        while (m) {
-            int b = __ffs(m) - 1;
-            m &= m - 1;
-            line_start[idx++] = (u32)(byte_base + u * 16ull + b + 1);
-        }
-        base += total;
-    }
-}
+#define K0_ST_AGG (1ull << 62)      // tile status: newline count of this tile
+#define K0_ST_PREFIX (2ull << 62)   // tile status: newline count of the chunk up to and including this tile
+#define K0_ST_VAL ((1ull << 62) - 1ull)
 
 struct K0Params {
     int phred_base;     // 33 | 64
@@ -81,81 +41,282 @@ struct K0Params {
     int max_len;        // 32 * W
 };
 
-// One thread per record.  Record r owns lines 4r .. 4r+3.
-template <int W>
-__global__ void __launch_bounds__(256)
-k0_pack(const unsigned char *__restrict__ text, const u32 *__restrict__ line_start, u64 n_records,
-        K0Params prm, u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta,
-        u32 *__restrict__ err_flags)
+// Carried from launch to launch (the regions of one chunk); lines[] alternates so that a launch
+// reads the slot its predecessor wrote while it writes the other one.
+struct K0State {
+    u64 lines[2];       // newlines of the chunk before the region
+    u64 nrec;           // records packed by the last launch (K1 reads it)
+};
+
+__device__ __forceinline__ u32 nl_mask_words(u32 x, u32 y, u32 z, u32 w)
+{
+    u32 m = 0;
+    const u32 v[4] = {x, y, z, w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const u32 eq = __vcmpeq4(v[k], 0x0A0A0A0Au);                 // 0xFF per matching byte
+        const u32 bits = ((eq & 0x01010101u) * 0x01020408u) >> 24;    // gather 4 flag bits
+        m |= (bits & 0xFu) << (4 * k);
+    }
+    return m;
+}
+
+__device__ __forceinline__ u64 k0_ld_status(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void k0_st_status(u64 *p, u64 v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// Packs one record.  F(off) returns the aligned 32-bit word at byte offset off (multiple of 4) and
+// B(off) one byte; offsets a0..a4 are the starts of the record's four lines and of the line after it.
+template <int W, typename F32, typename F8>
+__device__ __forceinline__ void k0_pack_record(F32 ld32, F8 ld8, u32 a0, u32 a1, u32 a2, u32 a3, u32 a4, const K0Params &prm,
+                                               u64 *s, u64 *nm, u32 &meta, u32 &bad)
 {
     const int NW = W / 2;
-    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_records; r += (u64)gridDim.x * blockDim.x) {
-        const u32 *ls = line_start + 4 * r;
-        u32 a0 = ls[0], a1 = ls[1], a2 = ls[2], a3 = ls[3], a4 = ls[4];
-        u32 bad = 0;
-        if (text[a0] != '@' || text[a2] != '+') bad |= ERRF_FORMAT;   // cutadapt FormatError
-        int sl = (int)(a2 - 1 - a1), ql = (int)(a4 - 1 - a3);
-        while (sl > 0 && text[a1 + sl - 1] == '\r') sl--;
-        while (ql > 0 && text[a3 + ql - 1] == '\r') ql--;
-        if (sl != ql) bad |= ERRF_FORMAT;
-        if (sl > prm.max_len) { bad |= ERRF_TOOLONG; sl = 0; ql = 0; }
-        u64 s[W], nm[NW];
+    bad = 0;
+    if (ld8(a0) != '@' || ld8(a2) != '+') bad |= ERRF_FORMAT;       // cutadapt FormatError
+    int sl = (int)(a2 - 1 - a1), ql = (int)(a4 - 1 - a3);
+    while (sl > 0 && ld8(a1 + sl - 1) == '\r') sl--;
+    while (ql > 0 && ld8(a3 + ql - 1) == '\r') ql--;
+    if (sl != ql) bad |= ERRF_FORMAT;
+    if (sl > prm.max_len) { bad |= ERRF_TOOLONG; sl = 0; ql = 0; }
 #pragma unroll
-        for (int w = 0; w < W; w++) s[w] = 0;
+    for (int w = 0; w < W; w++) s[w] = 0;
 #pragma unroll
-        for (int w = 0; w < NW; w++) nm[w] = 0;
-        if (!bad && sl > 0) {
-            // four bases per step: aligned 32-bit loads, realigned with a funnel shift;
-            // 2-bit codes and the non-ACGT flags are computed on all four bytes at once
-            const u32 *t32 = reinterpret_cast<const u32 *>(text) + (a1 >> 2);
-            const u32 sh8 = (a1 & 3u) * 8u;
-            u32 wprev = __ldg(t32);
-            const int ngroups = (sl + 3) >> 2;
+    for (int w = 0; w < NW; w++) nm[w] = 0;
+    if (!bad && sl > 0) {
+        const u32 t0 = a1 & ~3u;
+        const u32 sh8 = (a1 & 3u) * 8u;
+        u32 wprev = ld32(t0);
+        const int ngroups = (sl + 3) >> 2;
 #pragma unroll
-            for (int w = 0; w < W; w++) {
-                u64 acc = 0;
-                u32 nacc = 0;
-                for (int gi = w * 8; gi < w * 8 + 8 && gi < ngroups; gi++) {
-                    const u32 wnext = __ldg(t32 + gi + 1);
-                    const u32 v = __funnelshift_r(wprev, wnext, sh8);       // bytes a1+4gi .. a1+4gi+3
-                    wprev = wnext;
-                    const u32 up = v & 0xDFDFDFDFu;
-                    const u32 ok = __vcmpeq4(up, 0x41414141u) | __vcmpeq4(up, 0x43434343u) | __vcmpeq4(up, 0x47474747u) |
-                                   __vcmpeq4(up, 0x54545454u) | __vcmpeq4(up, 0x55555555u);        // A C G T U
-                    u32 code = (((v >> 1) ^ (v >> 2)) & 0x03030303u) & ok;   // A=0 C=1 G=2 T/U=3, others 0
-                    u32 packed = (code * 0x01041040u) >> 24;                  // 4 x 2 bits
-                    u32 nbits = (((~ok) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
-                    const int left = sl - gi * 4;
-                    if (left < 4) { packed &= (1u << (2 * left)) - 1u; nbits &= (1u << left) - 1u; }
-                    acc |= (u64)packed << ((gi & 7) * 8);
-                    nacc |= nbits << ((gi & 7) * 4);
+        for (int w = 0; w < W; w++) {
+            u64 acc = 0;
+            u32 nacc = 0;
+            for (int gi = w * 8; gi < w * 8 + 8 && gi < ngroups; gi++) {
+                const u32 wnext = ld32(t0 + 4u * (u32)(gi + 1));
+                const u32 v = __funnelshift_r(wprev, wnext, sh8);       // bytes a1+4gi .. a1+4gi+3
+                wprev = wnext;
+                const u32 up = v & 0xDFDFDFDFu;
+                const u32 ok = __vcmpeq4(up, 0x41414141u) | __vcmpeq4(up, 0x43434343u) | __vcmpeq4(up, 0x47474747u) |
+                               __vcmpeq4(up, 0x54545454u) | __vcmpeq4(up, 0x55555555u);        // A C G T U
+                const u32 code = (((v >> 1) ^ (v >> 2)) & 0x03030303u) & ok;   // A=0 C=1 G=2 T/U=3, others 0
+                u32 packed = (code * 0x01041040u) >> 24;                        // 4 x 2 bits
+                u32 nbits = (((~ok) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
+                const int left = sl - gi * 4;
+                if (left < 4) { packed &= (1u << (2 * left)) - 1u; nbits &= (1u << left) - 1u; }
+                acc |= (u64)packed << ((gi & 7) * 8);
+                nacc |= nbits << ((gi & 7) * 4);
+            }
+            s[w] = acc;
+            nm[w >> 1] |= (u64)nacc << ((w & 1) * 32);
+        }
+    }
+    // quality_trim_index(qualities, cutoff_front=0, cutoff_back, base)
+    int start = 0, stop = sl;
+    if (!bad) {
+        int acc = 0, mx = 0;
+        for (int i = 0; i < sl; i++) {
+            acc += 0 - ((int)ld8(a3 + i) - prm.phred_base);
+            if (acc < 0) break;
+            if (acc > mx) { mx = acc; start = i + 1; }
+        }
+        acc = 0; mx = 0;
+        for (int i = sl - 1; i >= 0; i--) {
+            acc += prm.qual_cutoff - ((int)ld8(a3 + i) - prm.phred_base);
+            if (acc < 0) break;
+            if (acc > mx) { mx = acc; stop = i; }
+        }
+        if (start >= stop) { start = 0; stop = 0; }
+    }
+    meta = (u32)sl | ((u32)start << 8) | ((u32)stop << 16);
+}
+
+// text: start of the chunk; the launch covers bytes [reg_start, reg_end) of it (reg_start a multiple
+// of K0_TILE); vnl: the chunk's last line has no '\n' -- a virtual one sits at byte reg_end (last
+// region only).  ctl[0] = tile ticket, ctl[1 + t] = status of tile t (zeroed before the launch).
+// par: which K0State::lines slot holds the count carried in.  Record r of the chunk (lines 4r..4r+3)
+// goes to slot r - (lines_in >> 2) of the output arrays.  last_region: the chunk ends with this
+// launch, so the line count must be a multiple of four.
+template <int W>
+__global__ void __launch_bounds__(K0_THREADS)
+k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end, int vnl, int last_region, u32 ntiles,
+              u64 *__restrict__ ctl, K0State *__restrict__ state, int par, K0Params prm, u64 rec_cap,
+              u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta, u32 *__restrict__ err_flags,
+              u64 *__restrict__ processed)
+{
+    constexpr int NW = W / 2;
+    __shared__ __align__(16) unsigned char buf[K0_HALO + K0_TILE + 16];
+    __shared__ __align__(16) u16 m16[K0_UNITS + 8];
+    __shared__ u16 lst[K0_CAP];
+    __shared__ u32 sh_scan[33];
+    __shared__ u32 sh_tile;
+    __shared__ u64 sh_excl;
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u64 lines_in = state->lines[par];
+    const u64 rec0 = lines_in >> 2;
+    u64 *status = ctl + 1;
+    for (;;) {
+        if (tid == 0) sh_tile = (u32)atomicAdd(ctl, 1ull);
+        __syncthreads();
+        const u32 tile = sh_tile;
+        if (tile >= ntiles) break;
+        const u64 tile_start = reg_start + (u64)tile * K0_TILE;
+        const i64 halo_start = (i64)tile_start - K0_HALO;
+        // ---- 1. load halo + tile, newline masks
+        for (int u = tid; u < K0_UNITS; u += K0_THREADS) {
+            const i64 g0 = halo_start + 16 * (i64)u;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            u32 m = 0;
+            if (g0 >= 0 && (u64)g0 < reg_end) {
+                if ((u64)g0 + 16 <= reg_end) {
+                    v = __ldg(reinterpret_cast<const uint4 *>(text + g0));
+                } else {                                     // the chunk's last, partial unit: byte loads only
+                    u32 w4[4] = {0, 0, 0, 0};
+                    for (int b = 0; (u64)g0 + b < reg_end; b++) w4[b >> 2] |= (u32)text[g0 + b] << ((b & 3) * 8);
+                    v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                 }
-                s[w] = acc;
-                nm[w >> 1] |= (u64)nacc << ((w & 1) * 32);
+                m = nl_mask_words(v.x, v.y, v.z, v.w);
+                const u64 rem = reg_end - (u64)g0;
+                if (rem < 16) m &= (1u << rem) - 1u;
+            }
+            if (vnl && g0 <= (i64)reg_end && (i64)reg_end < g0 + 16) m |= 1u << (u32)((i64)reg_end - g0);
+            *reinterpret_cast<uint4 *>(buf + 16 * u) = v;
+            m16[u] = (u16)m;
+        }
+        __syncthreads();
+        // ---- 2. rank the tile's newlines; chained scan over the tiles
+        const uint4 mm = *reinterpret_cast<const uint4 *>(m16 + K0_HALO / 16 + 8 * tid);   // this thread's 128 bytes
+        const u32 mw[4] = {mm.x, mm.y, mm.z, mm.w};
+        const u32 cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
+        u32 T;
+        const u32 ex = block_excl_scan(cnt, sh_scan, &T);
+        if (wid == 0) {
+            u64 excl = lines_in;
+            if (tile > 0) {
+                if (lane == 0) k0_st_status(status + tile, K0_ST_AGG | (u64)T);
+                excl = 0;
+                i64 look = (i64)tile - 1;
+                for (;;) {
+                    const i64 idx = look - lane;
+                    u64 s = idx >= 0 ? k0_ld_status(status + idx) : K0_ST_PREFIX;      // below tile 0: nothing to add
+                    const unsigned pm = __ballot_sync(0xffffffffu, (s >> 62) == 2ull);
+                    const unsigned im = __ballot_sync(0xffffffffu, (s >> 62) == 0ull);
+                    const int fp = pm ? __ffs(pm) - 1 : 32;
+                    const unsigned need = fp < 31 ? ((2u << fp) - 1u) : 0xffffffffu;
+                    if (im & need) continue;                 // a tile in the window has not published yet
+                    u64 val = ((int)lane <= fp) ? (s & K0_ST_VAL) : 0ull;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                    excl += val;
+                    if (fp < 32) break;
+                    look -= 32;
+                }
+            }
+            if (lane == 0) {
+                k0_st_status(status + tile, K0_ST_PREFIX | (excl + T));
+                sh_excl = excl;
             }
         }
-        // quality_trim_index(qualities, cutoff_front=0, cutoff_back, base)
-        int start = 0, stop = sl;
-        if (!bad) {
-            int acc = 0, mx = 0;
-            for (int i = 0; i < sl; i++) {
-                acc += 0 - ((int)text[a3 + i] - prm.phred_base);
-                if (acc < 0) break;
-                if (acc > mx) { mx = acc; start = i + 1; }
+        // ---- 3 + 4. line-start list, then the records that end in this tile
+        const i64 delta = halo_start;                        // global offset = shared offset + delta
+        for (u32 pass_lo = 0; pass_lo == 0 || pass_lo < T; pass_lo += K0_CAP - 4) {
+            {
+                u32 o = ex;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    u32 m = mw[k];
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const u32 li = o + 4 - pass_lo;
+                        if (li < K0_CAP) lst[li] = (u16)(K0_HALO + 128 * tid + 32 * k + b + 1);
+                        o++;
+                    }
+                }
             }
-            acc = 0; mx = 0;
-            for (int i = sl - 1; i >= 0; i--) {
-                acc += prm.qual_cutoff - ((int)text[a3 + i] - prm.phred_base);
-                if (acc < 0) break;
-                if (acc > mx) { mx = acc; stop = i; }
+            if (pass_lo == 0 && tid == 32) {                 // the halo's last four newlines (warp 1 while warp 0 looks back)
+                int found = 0;
+                if (tile_start == 0) { lst[3] = (u16)K0_HALO; found = 1; }     // the chunk's first line
+                else {
+                    for (int u = K0_HALO / 16 - 1; u >= 0 && found < 4; u--) {
+                        u32 m = m16[u];
+                        while (m && found < 4) {
+                            const int b = 31 - __clz(m);
+                            m &= ~(1u << b);
+                            lst[3 - found] = (u16)(16 * u + b + 1);
+                            found++;
+                        }
+                    }
+                }
+                for (; found < 4; found++) lst[3 - found] = K0_NONE;
             }
-            if (start >= stop) { start = 0; stop = 0; }
+            __syncthreads();
+            const u64 G = sh_excl;
+            const u32 o0 = (u32)((3ull - (G & 3ull)) & 3ull);        // first record-terminating newline of the tile
+            const u32 lo = pass_lo > o0 ? pass_lo + ((o0 + 4 - (pass_lo & 3)) & 3) : o0;
+            u32 hi = pass_lo + K0_CAP - 4;
+            if (hi > T) hi = T;
+            for (u32 o = lo + 4 * tid; o < hi; o += 4 * K0_THREADS) {
+                const u64 slot = ((G + o) >> 2) - rec0;
+                const u32 li = o + 4 - pass_lo;
+                u32 l[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) l[k] = lst[li - 4 + k];
+                u64 s[W], nm[NW];
+                u32 mt, bad;
+                if (l[0] != K0_NONE) {
+                    const unsigned char *b0 = buf;
+                    auto ld32 = [b0](u32 off) { return *reinterpret_cast<const u32 *>(b0 + off); };
+                    auto ld8 = [b0](u32 off) { return (u32)b0[off]; };
+                    k0_pack_record<W>(ld32, ld8, l[0], l[1], l[2], l[3], l[4], prm, s, nm, mt, bad);
+                } else {
+                    // a line of this record starts before the halo: find the missing starts in global memory
+                    u64 g[5];
+                    g[4] = (u64)((i64)l[4] + delta);
+                    for (int k = 3; k >= 0; k--) {
+                        if (l[k] != K0_NONE) { g[k] = (u64)((i64)l[k] + delta); continue; }
+                        u64 p = g[k + 1] - 1;                // the newline that ends line k
+                        while (p > 0 && text[p - 1] != '\n') p--;
+                        g[k] = p;
+                    }
+                    const u64 gb = g[0] & ~3ull;
+                    const unsigned char *tb = text + gb;
+                    const u64 lim = reg_end;
+                    auto ld8 = [tb, gb, lim](u32 off) { return gb + off < lim ? (u32)tb[off] : 0u; };
+                    auto ld32 = [ld8](u32 off) { return ld8(off) | (ld8(off + 1) << 8) | (ld8(off + 2) << 16) | (ld8(off + 3) << 24); };
+                    if (g[4] - gb >= 0xFFFFFF00ull) { bad = ERRF_FORMAT; mt = 0; for (int w = 0; w < W; w++) s[w] = 0; for (int w = 0; w < NW; w++) nm[w] = 0; }
+                    else k0_pack_record<W>(ld32, ld8, (u32)(g[0] - gb), (u32)(g[1] - gb), (u32)(g[2] - gb), (u32)(g[3] - gb), (u32)(g[4] - gb),
+                                           prm, s, nm, mt, bad);
+                }
+                if (bad) atomicOr(err_flags, bad);
+                if (slot < rec_cap) {
+                    if (W == 2) *reinterpret_cast<ulonglong2 *>(bases + slot * 2) = make_ulonglong2(s[0], s[1]);
+                    else {
+#pragma unroll
+                        for (int w = 0; w < W; w++) bases[slot * W + w] = s[w];
+                    }
+#pragma unroll
+                    for (int w = 0; w < NW; w++) nmask[slot * NW + w] = nm[w];
+                    meta[slot] = mt;
+                } else atomicOr(err_flags, ERRF_FORMAT);
+            }
+            __syncthreads();
         }
-        if (bad) atomicOr(err_flags, bad);
-#pragma unroll
-        for (int w = 0; w < W; w++) bases[r * W + w] = s[w];
-#pragma unroll
-        for (int w = 0; w < NW; w++) nmask[r * NW + w] = nm[w];
-        meta[r] = (u32)sl | ((u32)start << 8) | ((u32)stop << 16);
+        if (tile == ntiles - 1 && tid == 0) {                // hand the line count on to the next launch
+            const u64 lines_out = sh_excl + T;
+            state->lines[par ^ 1] = lines_out;
+            const u64 nrec = (lines_out >> 2) - rec0;
+            state->nrec = nrec;
+            atomicAdd(processed, nrec);
+            if (last_region && (lines_out & 3ull)) atomicOr(err_flags, ERRF_PARTIAL);
+        }
+        __syncthreads();
     }
 }

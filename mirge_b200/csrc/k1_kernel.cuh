@@ -460,7 +460,7 @@ __device__ __forceinline__ void k1_teardown(u32 my_kept, u32 my_diag, u64 *diag,
 template <int W>
 __global__ void __launch_bounds__(K1A_THREADS)
 k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-                 u64 n_records, int sample, TrimParams tp_param, K1Pre pre_param, TableView<W> T, K1Counters ctr, K1Queues Q,
+                 const u64 *__restrict__ n_records_ptr, int sample, TrimParams tp_param, K1Pre pre_param, TableView<W> T, K1Counters ctr, K1Queues Q,
                  int force_slow)
 {
     __shared__ u32 sh_hist[K1_HIST(W)];
@@ -473,6 +473,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
     for (int b = threadIdx.x; b < (int)(sizeof(K1Pre) / 4); b += K1A_THREADS)
         reinterpret_cast<u32 *>(&pre)[b] = reinterpret_cast<const u32 *>(&pre_param)[b];
     __syncthreads();
+    const u64 n_records = *n_records_ptr;                  // written by K0 (K0State::nrec)
     const bool use_pre = pre.enabled && !(force_slow & 4);
     const int mode = tp_param.mode, uncond = tp_param.uncond, min_length = tp_param.min_length;
     const u64 aw0 = tp_param.aw[0][0];

@@ -147,7 +147,9 @@ def test_error_paths():
     e.set_adapter(ILLUMINA)
     with pytest.raises(MirgeError) as ei:
         e.feed_fastq(0, b'@r\nACGT\n+\nIIII\n@r2\nACGT\n+\n', 33)     # 7 lines
-    assert ei.value.code == -3
+        e.sync()                                                        # lines are counted on the device: surfaces at the next sync
+    assert ei.value.code == -3 and 'whole number' in str(ei.value)
+    e.reset()
     e.feed_fastq(0, b'@r\nACGT\n+\nIII\n', 33)                         # quality shorter than sequence
     with pytest.raises(MirgeError) as ei:
         e.sync()
