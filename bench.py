@@ -87,16 +87,33 @@ class ClockSampler(threading.Thread):
 
 
 def ncu_traffic(kernel, n_reads):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture of this workload, else None."""
-    path = os.path.join(ROOT, 'profiles', 'r1_k1_full_metrics.txt')
-    if kernel != 'k1_trim_collapse' or n_reads != 25_000_000 or not os.path.exists(path):
+    """dram bytes per step of kernel family `kernel` from the committed ncu --set full capture of THIS workload
+    (profiles/r2_traffic.json, written by profiles/summarize_ncu.py from the capture named inside), else None."""
+    path = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if n_reads != 25_000_000 or not os.path.exists(path):
         return None
-    tot = 0.0
-    for line in open(path):
-        f = line.split()
-        if len(f) >= 3 and f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-            tot += float(f[1]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[f[2]]
-    return tot or None
+    try:
+        return json.load(open(path)).get('dram_bytes_per_step', {}).get(kernel)
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(gpu):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity) BEFORE pinned host memory is allocated, so
+    first-touch places the staging buffers on the GPU's NUMA node: at 8 ranks the H2D copies otherwise cross the
+    socket interconnect (round 1: 49 GB/s per GPU at N=1, 21 GB/s at N=8)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
 
 
 def build_world(args):
@@ -175,24 +192,57 @@ def algorithmic_bytes(kernel, n_reads, kept, n_unique, text_bytes, rounds_proces
     """Algorithmic HBM bytes per step for one kernel family."""
     if kernel == 'k1_trim_collapse':
         return 28 * n_reads + 40 * kept + 60 * n_unique
-    if kernel == 'k0_pack':
-        return text_bytes + 28 * n_reads + 20 * n_reads
-    if kernel in ('k0_count_newlines', 'k0_line_starts'):
-        return text_bytes + (16 * n_reads if kernel == 'k0_line_starts' else 0)
-    if kernel.startswith('k2_round'):
-        return 130 * rounds_processed
+    if kernel == 'k0_parse_pack':
+        return text_bytes + 28 * n_reads          # the text once in, one packed record out
+    if kernel == 'k2_rounds':
+        return 130 * rounds_processed             # SURVEY.md 8(d): ~130 B per (unique sequence x round)
     return None
 
 
+def tables_checksum(tabs):
+    import hashlib
+    h = hashlib.sha256()
+    for k in ('mir_quant', 'mir_iscan', 'lib_totals', 'len_hist'):
+        h.update(np.ascontiguousarray(tabs[k]).astype(np.int64).tobytes())
+    return h.hexdigest()[:16]
+
+
+EQ_CHUNKS, EQ_READS = 8, 50_000      # the fixed equality job: 8 samples of 50k reads, dealt round-robin to the ranks
+
+
+def equality_job(world_obj, make_engine, rank, N, dev, reduce_fn, partition_fn):
+    """A fixed small job whose reduced tables must not depend on N: 8 samples x 50k reads, sample s trimmed by rank
+    s % N, hash partition, annotate, tally, device all-reduce.  Returns the checksum of the job-wide tables."""
+    eng = make_engine(EQ_CHUNKS)
+    for s in range(EQ_CHUNKS):
+        if s % N == rank:
+            eng.feed_fastq(s, world_obj.fastq(EQ_READS, seed=2000 + s, L=READ_LEN), 33)
+    if N > 1:
+        partition_fn(eng)
+    eng.annotate()
+    eng.tally()
+    if N > 1:
+        reduce_fn(eng)
+    tabs = eng.export_tables()
+    p, k, _ = eng.stats()
+    assert int(p.sum()) == EQ_CHUNKS * EQ_READS, 'equality job: processed != reads fed'
+    assert int(tabs['lib_totals'][:, 1:11].sum()) == int(k.sum()), 'equality job: library totals do not add up to kept reads'
+    eng.sync()
+    cs = tables_checksum(tabs)
+    eng.close()
+    return cs
+
+
 def run_ours(args):
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world_size = int(os.environ.get('WORLD_SIZE', '1'))
+    n_cpus_bound = bind_to_gpu_numa_node(local_rank)      # before torch allocates pinned memory
     import torch
     import torch.distributed as dist
     from mirge_b200.engine import Engine, LIB_IDS
     from mirge_b200 import dist as mdist
 
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    world_size = int(os.environ.get('WORLD_SIZE', '1'))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world_size > 1:
@@ -208,13 +258,18 @@ def run_ours(args):
     world.fastq(n_reads, seed=1000 + rank, L=READ_LEN, out=host.numpy())
     dev_text = host.to(dev)
     # a rank holds its own sample's uniques before the exchange (0.32 per read on this workload) and at most
-    # total/N of them after it, so the single-GPU bound serves every N (a larger table only costs memset time)
+    # total/N of them after it, so the single-GPU bound serves every N
     max_unique = args.max_unique or max(1 << 20, int(n_reads * 0.6))
-    eng = Engine(S, False, max_unique, 64, device=local_rank)
-    eng.set_adapter(ADAPTER)
-    load_libs(eng, world, LIB_IDS)
     stream = torch.cuda.Stream(device=dev)
-    eng.set_stream(stream.cuda_stream)
+
+    def make_engine(n_samples):
+        e = Engine(n_samples, False, max_unique if n_samples == S else (1 << 20), 64, device=local_rank)
+        e.set_adapter(ADAPTER)
+        load_libs(e, world, LIB_IDS)
+        e.set_stream(stream.cuda_stream)
+        return e
+
+    eng = make_engine(S)
     sample = rank
 
     def step(resident):
@@ -224,15 +279,12 @@ def run_ours(args):
         else:
             eng.feed_fastq(sample, host.numpy(), 33)
         if N > 1:
-            mdist.hash_partition(eng)
+            mdist.hash_partition(eng)                # X1
         eng.annotate()
         eng.tally()
-        tables = None
-        if not resident:
-            tables = eng.export_tables()     # D2H of the step's result
-            if N > 1:
-                tables = mdist.reduce_tables({k: tables[k] for k in ('mir_quant', 'mir_iscan', 'lib_totals')}, dev)
-        return tables
+        if N > 1:
+            mdist.reduce_engine_tables(eng)          # X2, on the device, inside the timed region of both modes
+        return eng.export_tables() if not resident else None     # D2H of the step's result
 
     def timed(resident, steps, warmup, profile=False):
         with torch.cuda.stream(stream):
@@ -266,62 +318,88 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_res, launches, prof = timed(True, args.steps, args.warmup, profile=True)
-    # size-independent correctness properties at full size (tests/ hold the bit-exact oracle comparisons)
+    # size-independent correctness properties at full size (tests/ hold the bit-exact oracle comparisons): after the
+    # reduction every rank holds the job-wide tables
     p, k, U = eng.stats()
     slow_frac = eng.slow_reads() / float(n_reads)
     cls = eng.trim_classes()
     tabs = eng.export_tables()
-    if N > 1:
-        tabs = mdist.reduce_tables({kk: tabs[kk] for kk in ('lib_totals',)}, dev)
     tot = tabs['lib_totals']
-    assert int(p[sample]) == n_reads, 'processed != reads fed'
-    if N == 1:
-        assert int(tot[sample, 1:11].sum()) == int(k[sample]), 'library totals do not add up to kept reads'
+    assert int(p[sample]) == n_reads and int(p.sum()) == n_reads * N, 'processed != reads fed'
+    assert int(tot[:, 1:11].sum()) == int(k.sum()), 'library totals do not add up to kept reads'
+    assert int(tabs['len_hist'].sum()) == int(k.sum()), 'read-length histogram does not add up to kept reads'
+    rounds_proc_all = tabs['round_processed']
     ms_e2e, _, _ = timed(False, args.steps, max(3, args.warmup))
     sampler.stop()
     d2h = sum(int(np.asarray(v).nbytes) for v in eng.export_tables().values())
     total_reads = n_reads * N
     value = total_reads * args.steps / (ms_res / 1e3)
     e2e = total_reads * args.steps / (ms_e2e / 1e3)
+    # the fixed equality job: its checksum must be the same at every N (and equal the oracle's, checked at N=1 below)
+    with torch.cuda.stream(stream):
+        eq_sum = equality_job(world, make_engine, rank, N, dev, mdist.reduce_engine_tables, mdist.hash_partition)
 
-    roof = None
-    cpu = None
     if rank == 0:
         peaks = {}
         pk_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(pk_path):
             peaks = json.load(open(pk_path))
         peak = float(peaks.get('hbm_gbs', 6650.0))
-        fam = {n: v for n, v in prof.items() if n.startswith('k') and v[1] > 0 and not n.startswith(('k1a', 'k1b', 'k1c', 'k1d'))}   # k1a..k1d are the four launches of the k1_trim_collapse family
-        dom = max(fam, key=lambda n: fam[n][0])
-        dom_ms, dom_n = fam[dom]
-        rounds_proc = int(eng.export_tables()['round_processed'][int(dom[len('k2_round')])]) if dom.startswith('k2_round') else 0
-        ab = algorithmic_bytes(dom, n_reads, int(k[sample]), U, nbytes, rounds_proc)
-        per_launch_bytes = ab * args.steps / dom_n if ab else None
-        per_launch_ms = dom_ms / dom_n
-        ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if ab else None
-        roof = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                'frac': (ach / peak) if ach else None, 'traffic': ncu_traffic(dom, n_reads),
-                'algorithmic_bytes_per_launch': per_launch_bytes,
+        per_step = {n: v[0] / args.steps for n, v in prof.items() if v[1] > 0}
+        # kernel families: k1a..k1d are the launches of k1_trim_collapse; the mapping rounds are one family
+        fam_ms = {'k0_parse_pack': per_step.get('k0_parse_pack', 0.0), 'k1_trim_collapse': per_step.get('k1_trim_collapse', 0.0),
+                  'k2_rounds': sum(v for n, v in per_step.items() if n.startswith('k2_round')),
+                  'k3_tally': sum(v for n, v in per_step.items() if n.startswith('k3_'))}
+        rounds_proc = int(np.asarray(rounds_proc_all).sum())
+        fam = {}
+        for name, ms in fam_ms.items():
+            ab = algorithmic_bytes(name, n_reads, int(k[sample]), U, nbytes, rounds_proc)
+            fam[name] = {'ms_per_step': round(ms, 4), 'algorithmic_bytes_per_step': ab,
+                         'achieved_gbs': (ab / (ms * 1e-3) / 1e9) if (ab and ms > 0) else None,
+                         'frac': (ab / (ms * 1e-3) / 1e9 / peak) if (ab and ms > 0) else None,
+                         'traffic': ncu_traffic(name, n_reads)}
+        dom = max(fam_ms, key=lambda n: fam_ms[n])
+        roof = {'bound': 'hbm', 'kernel': dom, 'achieved': fam[dom]['achieved_gbs'], 'peak': peak, 'unit': 'GB/s',
+                'frac': fam[dom]['frac'], 'traffic': fam[dom]['traffic'],
+                'algorithmic_bytes_per_launch': fam[dom]['algorithmic_bytes_per_step'],
+                'launch_unit': 'one kernel family per step (k1_trim_collapse = its 3-4 launches per feed region; k2_rounds = the 9 round kernels)',
                 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)',
-                'kernel_ms_per_step': {n: round(v[0] / args.steps, 4) for n, v in prof.items() if v[1] > 0},
-                'share_of_step': dom_ms / ms_res}
-        sample_reads = min(n_reads, args.cpu_sample)
-        cv, csec, cores = cpu_run(world, sample_reads, 1, 0, 1000)
-        cpu = {'value': cv, 'unit': 'reads/s', 'cores': cores, 'kind': 'port',
-               'sample': 'first %d reads of the workload, one pass (trim+collapse+9 rounds+tally), oracle C port with OpenMP' % sample_reads}
+                'families': fam, 'kernel_ms_per_step': {n: round(v, 4) for n, v in per_step.items()},
+                'share_of_step': fam_ms[dom] / (ms_res / args.steps)}
+        cpu = None
+        if N == 1:
+            sample_reads = min(n_reads, args.cpu_sample)
+            cv, csec, cores = cpu_run(world, sample_reads, 1, 0, 1000)
+            cpu = {'value': cv, 'unit': 'reads/s', 'cores': cores, 'kind': 'port',
+                   'sample': 'first %d reads of the workload, one pass (trim+collapse+9 rounds+tally), oracle C port with OpenMP' % sample_reads,
+                   'equality_checksum_matches_oracle': oracle_equality_checksum(world) == eq_sum}
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'reads/s', 'n_gpus': N, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u8/u64 (2-bit packed integer)', 'data': 'synthetic',
-            'config': {'workload': workload_name(args), 'reads_per_gpu': n_reads, 'unique_per_gpu': U, 'kept_frac': float(k[sample]) / n_reads, 'k1_slow_path_frac': slow_frac, 'k1_class1_frac': cls[1] / float(n_reads), 'k1_class2_frac': cls[2] / float(n_reads),
+            'config': {'workload': workload_name(args), 'reads_per_gpu': n_reads, 'unique_owned_rank0': U, 'kept_frac': float(k[sample]) / n_reads, 'k1_slow_path_frac': slow_frac, 'k1_class1_frac': cls[1] / float(n_reads), 'k1_class2_frac': cls[2] / float(n_reads),
                        'l2_policy': 'inputs (%.2f GB FASTQ text per GPU) larger than the 126 MB L2' % (nbytes / 1e9),
-                       'parallelism': 'reads sharded by sample across %d GPU(s); hash-partition all-to-all + table all-reduce' % N},
+                       'parallelism': 'reads sharded by sample across %d GPU(s); hash-partition all-to-all (X1) + device table all-reduce (X2), both inside the timed region' % N,
+                       'cpus_bound_to_gpu_numa_node': n_cpus_bound,
+                       'equality_job': '%d samples x %d reads dealt round-robin to the ranks; checksum of the reduced tables must not depend on N' % (EQ_CHUNKS, EQ_READS),
+                       'equality_checksum': eq_sum},
             'e2e': {'value': e2e, 'unit': 'reads/s', 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'clocks': sampler.summary(), 'roofline': roof, 'cpu_baseline': cpu,
         }))
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def oracle_equality_checksum(world_obj):
+    """The equality job on the CPU oracle (cpu_baseline leg, N=1 only): the checker for the GPU checksum."""
+    from oracle import oracle as O
+    o = O.Oracle(EQ_CHUNKS, False, ADAPTER, threads=os.cpu_count() or 1)
+    load_libs(o, world_obj, O.LIB_IDS)
+    for s in range(EQ_CHUNKS):
+        o.feed_fastq(s, world_obj.fastq(EQ_READS, seed=2000 + s, L=READ_LEN).tobytes(), 33)
+    o.annotate()
+    q, i, t = o.tally()
+    return tables_checksum({'mir_quant': q, 'mir_iscan': i, 'lib_totals': t, 'len_hist': o.len_hist(64)})
 
 
 def main():

@@ -131,16 +131,27 @@ int mirge_export_tables(mirge_ctx *ctx, int64_t *mir_quant, int64_t *mir_iscan, 
 
 /* -- multi-GPU exchange (no reference counterpart; samples are serial there) */
 
-/* Bytes of one exchange record: packed key + length + S counts. */
+/* Bytes of one exchange record: packed key, then len | sample << 8 and the read
+ * count of that sample (32 bytes for reads <= 64 nt). */
 int mirge_record_bytes(const mirge_ctx *ctx);
-/* Write every unique sequence as a record into dev_buf, grouped by owner
- * rank = hash(key) % n_parts; part_counts[n_parts] (host) receives the group
- * sizes.  Synchronises. */
-int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint64_t cap_records, uint64_t *part_counts);
+/* X1, sender side: write every (unique sequence, sample) pair with
+ * a non-zero count as a record into dev_buf (capacity cap_records), grouped by
+ * owner rank = hash(key) % n_parts; part_counts_dev[n_parts] (DEVICE memory)
+ * receives the group sizes.  Asynchronous on the context's stream: no host
+ * round trip, the caller moves the sizes and the records with its transport
+ * (mirge_b200/dist.py: torch.distributed all-to-all over NCCL). */
+int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint64_t cap_records, uint64_t *part_counts_dev);
 /* Forget all unique sequences (per-sample processed/kept and len_hist stay). */
 int mirge_reset_unique(mirge_ctx *ctx);
-/* Insert n_records received records, adding their counts. */
+/* X1, owner side: insert n_records received records, adding their counts. */
 int mirge_import_records_device(mirge_ctx *ctx, const void *dev_buf, uint64_t n_records);
+/* X2: the integer tables of this rank -- mir_quant, mir_iscan,
+ * lib_totals, len_hist, kept, processed, in this order -- as one contiguous
+ * int64 vector of mirge_tables_words() words in device memory, for an in-place
+ * sum over ranks (NCCL all-reduce), and back.  Asynchronous on the stream. */
+uint64_t mirge_tables_words(const mirge_ctx *ctx);
+int mirge_pack_tables_device(mirge_ctx *ctx, void *dst_dev);
+int mirge_unpack_tables_device(mirge_ctx *ctx, const void *src_dev);
 /* Owner hash of an ASCII sequence (for host-side tests of the partitioning). */
 uint64_t mirge_hash_sequence(const char *seq, int len);
 

@@ -48,6 +48,9 @@ _SIGS = {
     'mirge_export_records_device': (C.c_int, [ctx_p, C.c_int, vp, u64, vp]),
     'mirge_reset_unique': (C.c_int, [ctx_p]),
     'mirge_import_records_device': (C.c_int, [ctx_p, vp, u64]),
+    'mirge_tables_words': (u64, [ctx_p]),
+    'mirge_pack_tables_device': (C.c_int, [ctx_p, vp]),
+    'mirge_unpack_tables_device': (C.c_int, [ctx_p, vp]),
     'mirge_hash_sequence': (u64, [C.c_char_p, C.c_int]),
     'mirge_profile_enable': (C.c_int, [ctx_p, C.c_int]),
     'mirge_profile_read': (C.c_int, [ctx_p, vp, vp, vp]),

@@ -8,6 +8,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <ctype.h>
+#include <stddef.h>
 #include <string>
 #include <vector>
 
@@ -64,7 +65,8 @@ struct mirge_ctx {
     int force_slow = 0;
     // K0 scratch
     unsigned char *d_text = nullptr; size_t text_cap = 0;
-    u64 *d_k0ctl = nullptr; size_t k0ctl_cap = 0;   // tile ticket + tile statuses of the running K0 launch
+    u64 *d_k0ctl = nullptr; size_t k0ctl_cap = 0;   // exact path: tile ticket + tile statuses of the running launch
+    u32 *d_k0info = nullptr; size_t k0info_cap = 0; // speculative path: newline count | claim per tile
     K0State *d_k0state = nullptr;
     u64 *d_bases = nullptr, *d_nmask = nullptr; u32 *d_meta = nullptr; size_t rec_cap = 0;
     u64 *d_q1 = nullptr; u32 *d_q2 = nullptr, *d_q3 = nullptr; u64 *d_qn = nullptr, *d_part = nullptr;   // K1 class queues (rec_cap entries each), their fills; exchange partition counters
@@ -307,7 +309,7 @@ void mirge_destroy(mirge_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (int i = 0; i < MIRGE_N_LIBS; i++) free_lib(ctx->libs[i]);
-    cudaFree(ctx->d_text); cudaFree(ctx->d_k0ctl); cudaFree(ctx->d_k0state);
+    cudaFree(ctx->d_text); cudaFree(ctx->d_k0ctl); cudaFree(ctx->d_k0info); cudaFree(ctx->d_k0state);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
     cudaFree(ctx->d_q1); cudaFree(ctx->d_q2); cudaFree(ctx->d_q3); cudaFree(ctx->d_qn); cudaFree(ctx->d_part);
     cudaFree(ctx->d_slots); cudaFree(ctx->d_useq); cudaFree(ctx->d_unmask); cudaFree(ctx->d_ulen); cudaFree(ctx->d_counts);
@@ -398,7 +400,7 @@ int mirge_detect_phred(const char *buf, uint64_t n)
 }
 
 #define FEED_REGION_HOST (64ull << 20)      // H2D copy granularity: kernels of region r overlap the copy of region r+1
-#define FEED_REGION_DEVICE (256ull << 20)   // text already resident: fewer, larger launches
+#define FEED_REGION_DEVICE (1024ull << 20)  // text already resident: few, large launches (the K1 queue kernels have long tails)
 
 // Core of mirge_feed_fastq{,_device}: the chunk is consumed region by region, without any host
 // synchronisation.  With a host source every region's H2D copy is queued up front on the copy
@@ -456,19 +458,29 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
     }
     const u64 max_tiles = (max_region + 1 + K0_TILE - 1) / K0_TILE;
     CK(ensure(&ctx->d_k0ctl, &ctx->k0ctl_cap, max_tiles + 2));
+    CK(ensure(&ctx->d_k0info, &ctx->k0info_cap, max_tiles + 2));
     CK(cudaMemsetAsync(ctx->d_k0state, 0, sizeof(K0State), st));      // the chunk starts at line 0
-    const int k0_grid = wave_grid(k0_parse_pack<W>, K0_THREADS, ~0ull);
+    const int k0_grid = wave_grid(k0_parse_pack<W>, K0_THREADS, ~0ull), k0s_grid = wave_grid(k0_parse_spec<W>, K0_THREADS, ~0ull);
+    const bool exact_only = (ctx->force_slow & 0x2000) != 0;          // test hook: skip the speculation
+    u32 *err_flags = (u32 *)(ctx->d_ctr + 1);
+    u64 *processed = ctx->d_ctr + 5 + ctx->S + sample;
     for (int r = 0; r < nreg; r++) {
         const u64 a = (u64)r * region, len = (a + region <= nbytes) ? region : nbytes - a;
         if (host_src) CK(cudaStreamWaitEvent(st, ctx->copy_events[r], 0));
         const bool last = r == nreg - 1;
         const int vnl = (last && last_char != '\n') ? 1 : 0;       // unterminated final line
         const u32 ntiles = (u32)((len + vnl + K0_TILE - 1) / K0_TILE);
-        { ProfScope ps(ctx, KID_K0_PACK);
+        { ProfScope ps(ctx, KID_K0_PACK, exact_only ? 1 : 3);
+          CK(cudaMemsetAsync(&ctx->d_k0state->nrec, 0, sizeof(K0State) - offsetof(K0State, nrec), st));
           CK(cudaMemsetAsync(ctx->d_k0ctl, 0, ((size_t)ntiles + 1) * sizeof(u64), st));
+          if (!exact_only) {
+              k0_parse_spec<W><<<grid_for((u64)ntiles * K0_THREADS, K0_THREADS, k0s_grid), K0_THREADS, 0, st>>>(
+                  d_text, a, a + len, vnl, ntiles, ctx->d_k0info, ctx->d_k0state, kp, ctx->rec_cap, ctx->d_bases, ctx->d_nmask, ctx->d_meta);
+              k0_verify<<<1, 1024, 0, st>>>(ctx->d_k0info, ntiles, ctx->d_k0state, r & 1, last ? 1 : 0, err_flags, processed);
+          }
           k0_parse_pack<W><<<grid_for((u64)ntiles * K0_THREADS, K0_THREADS, k0_grid), K0_THREADS, 0, st>>>(
               d_text, a, a + len, vnl, last ? 1 : 0, ntiles, ctx->d_k0ctl, ctx->d_k0state, r & 1, kp, ctx->rec_cap,
-              ctx->d_bases, ctx->d_nmask, ctx->d_meta, (u32 *)(ctx->d_ctr + 1), ctx->d_ctr + 5 + ctx->S + sample); }
+              ctx->d_bases, ctx->d_nmask, ctx->d_meta, err_flags, processed, exact_only ? 1 : 0); }
         const u64 *nrec = &ctx->d_k0state->nrec;
         const u64 rec_bound = len / 6 + 1;                          // sizes the grids only
         { ProfScope ps(ctx, KID_K1_TRIM, 4);
@@ -812,8 +824,7 @@ int mirge_export_tables(mirge_ctx *ctx, int64_t *mir_quant, int64_t *mir_iscan, 
 // ---------------------------------------------------------------------------
 int mirge_record_bytes(const mirge_ctx *ctx)
 {
-    const int b = 8 * (ctx->W + ctx->W / 2) + 4 * (1 + ctx->S);
-    return (b + 7) & ~7;
+    return 8 * (ctx->W + ctx->W / 2) + 8;
 }
 
 __global__ void k_excl_scan_small(const u64 *in, u64 *out, int n)
@@ -822,32 +833,28 @@ __global__ void k_excl_scan_small(const u64 *in, u64 *out, int n)
     for (int i = 0; i < n; i++) { out[i] = acc; acc += in[i]; }
 }
 
-int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint64_t cap_records, uint64_t *part_counts)
+int mirge_export_records_device(mirge_ctx *ctx, int n_parts, void *dev_buf, uint64_t cap_records, uint64_t *part_counts_dev)
 {
-    if (n_parts < 1 || n_parts > 1024 || !part_counts) return fail(ctx, MIRGE_E_ARG, "mirge_export_records_device: bad argument");
-    u64 U = 0;
-    int rc = mirge_get_stats(ctx, nullptr, nullptr, (uint64_t *)&U);
-    if (rc) return rc;
-    if (cap_records < U) return fail(ctx, MIRGE_E_ARG, "mirge_export_records_device: buffer too small");
+    if (n_parts < 1 || n_parts > 1024 || !part_counts_dev || !dev_buf) return fail(ctx, MIRGE_E_ARG, "mirge_export_records_device: bad argument");
+    CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (!ctx->d_part) CK(cudaMalloc(&ctx->d_part, 2 * 1024 * sizeof(u64)));      // kept: cudaFree would synchronise the device every step
     u64 *d_cnt = ctx->d_part;
     CK(cudaMemsetAsync(d_cnt, 0, 2 * (size_t)n_parts * sizeof(u64), st));
-    const int rb = mirge_record_bytes(ctx), g = grid_for(U, 128, 148 * 8);
+    const int rb = mirge_record_bytes(ctx), g = grid_for(ctx->max_unique, 128, 148 * 8);
     {
         ProfScope ps(ctx, KID_EXCHANGE, 3);
         if (ctx->W == 2) {
-            k1_export_records<2><<<g, 128, 0, st>>>(table_view<2>(ctx), U, n_parts, rb, 1, d_cnt, nullptr, nullptr);
+            k1_export_records<2><<<g, 128, 0, st>>>(table_view<2>(ctx), n_parts, rb, 1, cap_records, d_cnt, nullptr, nullptr);
             k_excl_scan_small<<<1, 1, 0, st>>>(d_cnt, d_cnt + n_parts, n_parts);
-            k1_export_records<2><<<g, 128, 0, st>>>(table_view<2>(ctx), U, n_parts, rb, 0, d_cnt, d_cnt + n_parts, (unsigned char *)dev_buf);
+            k1_export_records<2><<<g, 128, 0, st>>>(table_view<2>(ctx), n_parts, rb, 0, cap_records, d_cnt, d_cnt + n_parts, (unsigned char *)dev_buf);
         } else {
-            k1_export_records<4><<<g, 128, 0, st>>>(table_view<4>(ctx), U, n_parts, rb, 1, d_cnt, nullptr, nullptr);
+            k1_export_records<4><<<g, 128, 0, st>>>(table_view<4>(ctx), n_parts, rb, 1, cap_records, d_cnt, nullptr, nullptr);
             k_excl_scan_small<<<1, 1, 0, st>>>(d_cnt, d_cnt + n_parts, n_parts);
-            k1_export_records<4><<<g, 128, 0, st>>>(table_view<4>(ctx), U, n_parts, rb, 0, d_cnt, d_cnt + n_parts, (unsigned char *)dev_buf);
+            k1_export_records<4><<<g, 128, 0, st>>>(table_view<4>(ctx), n_parts, rb, 0, cap_records, d_cnt, d_cnt + n_parts, (unsigned char *)dev_buf);
         }
     }
-    CK(cudaMemcpyAsync(part_counts, d_cnt, (size_t)n_parts * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(part_counts_dev, d_cnt, (size_t)n_parts * sizeof(u64), cudaMemcpyDeviceToDevice, st));
     CK(cudaGetLastError());
     return MIRGE_OK;
 }
@@ -889,8 +896,10 @@ int mirge_reset_unique(mirge_ctx *ctx)
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t esz = ctx->W == 2 ? sizeof(TEntry<2>) : sizeof(TEntry<4>);
+    ProfScope ps(ctx, KID_RESET);
     CK(cudaMemsetAsync(ctx->d_slots, 0, ctx->table_cap * esz, st));
-    CK(cudaMemsetAsync(ctx->d_counts, 0, ctx->max_unique * (size_t)ctx->S * sizeof(u32), st));
+    // count rows at or beyond the unique counter were never touched since the last clear
+    k1_clear_counts<<<grid_for(ctx->max_unique * (u64)ctx->S, 256, 148 * 8), 256, 0, st>>>(ctx->d_counts, ctx->d_ctr, ctx->max_unique, ctx->S);
     CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(u64), st));
     ctx->annotated = false; ctx->tallied = false;
     return MIRGE_OK;
@@ -906,6 +915,53 @@ int mirge_import_records_device(mirge_ctx *ctx, const void *dev_buf, uint64_t n_
     else k1_import_records<4><<<g, 128, 0, ctx->stream>>>((const unsigned char *)dev_buf, n_records, rb, table_view<4>(ctx));
     CK(cudaGetLastError());
     ctx->annotated = false; ctx->tallied = false;
+    return MIRGE_OK;
+}
+
+// Packed integer tables for the multi-GPU reduction (X2): everything a rank contributes to the report.
+static void table_pieces(mirge_ctx *ctx, void **ptr, size_t *words)
+{
+    const size_t nm = (size_t)ctx->libs[MIRGE_LIB_MIRNA].n_refs, S = (size_t)ctx->S;
+    ptr[0] = ctx->d_mir_quant; words[0] = nm * S;
+    ptr[1] = ctx->d_mir_iscan; words[1] = nm * S;
+    ptr[2] = ctx->d_lib_totals; words[2] = S * MIRGE_N_TOTALS;
+    ptr[3] = ctx->d_len_hist; words[3] = (size_t)(ctx->max_len + 1) * S;
+    ptr[4] = ctx->d_ctr + 2; words[4] = S;                  // kept
+    ptr[5] = ctx->d_ctr + 5 + S; words[5] = S;              // processed
+}
+
+uint64_t mirge_tables_words(const mirge_ctx *ctx)
+{
+    void *p[6]; size_t w[6];
+    table_pieces(const_cast<mirge_ctx *>(ctx), p, w);
+    return w[0] + w[1] + w[2] + w[3] + w[4] + w[5];
+}
+
+int mirge_pack_tables_device(mirge_ctx *ctx, void *dst_dev)
+{
+    if (!ctx->tallied) return fail(ctx, MIRGE_E_STATE, "mirge_pack_tables_device called before mirge_tally");
+    CK(cudaSetDevice(ctx->device));
+    void *p[6]; size_t w[6];
+    table_pieces(ctx, p, w);
+    i64 *d = (i64 *)dst_dev;
+    for (int k = 0; k < 6; k++) {
+        if (w[k]) CK(cudaMemcpyAsync(d, p[k], w[k] * sizeof(i64), cudaMemcpyDeviceToDevice, ctx->stream));
+        d += w[k];
+    }
+    return MIRGE_OK;
+}
+
+int mirge_unpack_tables_device(mirge_ctx *ctx, const void *src_dev)
+{
+    if (!ctx->tallied) return fail(ctx, MIRGE_E_STATE, "mirge_unpack_tables_device called before mirge_tally");
+    CK(cudaSetDevice(ctx->device));
+    void *p[6]; size_t w[6];
+    table_pieces(ctx, p, w);
+    const i64 *d = (const i64 *)src_dev;
+    for (int k = 0; k < 6; k++) {
+        if (w[k]) CK(cudaMemcpyAsync(p[k], d, w[k] * sizeof(i64), cudaMemcpyDeviceToDevice, ctx->stream));
+        d += w[k];
+    }
     return MIRGE_OK;
 }
 

@@ -6,19 +6,30 @@
 // string is consumed here, once, and only the (start, stop) trim window
 // travels on to K1.
 //
-// k0_parse_pack: a persistent grid takes 16 KiB tiles of the text in order (atomic ticket).  Per tile:
-//   1. coalesced 128-bit loads bring the tile plus a 1 KiB halo (the bytes before it) into shared
-//      memory; the '\n' mask of every 16-byte unit is computed on the way (SIMD byte compare);
-//   2. one block scan ranks the tile's newlines; their global rank -- which decides whether a line is
-//      a header, a sequence, a '+' or a quality line -- comes from a chained scan over the tiles with
-//      warp-wide decoupled look-back (status word = flag | count, one 64-bit store), seeded with the
-//      line count carried over from the previous launch (regions of one chunk are separate launches);
-//   3. every newline drops the start offset of the following line into a shared-memory list; the halo
-//      contributes its last four;
-//   4. one thread per record whose quality line ENDS in the tile packs it straight out of shared
-//      memory: aligned 32-bit loads realigned by funnel shift, four bases per step (2-bit codes and
-//      non-ACGT flags computed on all four bytes at once), quality_trim_index on both ends, format
-//      checks -> bases / nmask / meta, coalesced.
+// Which of a tile's lines are headers, sequences, '+' or quality lines depends on the number of
+// newlines BEFORE the tile -- a prefix sum over the whole text.  A chained scan settles it exactly
+// but moves its frontier only ~32 tiles per L2 round trip, far too slowly for 16 KiB tiles at HBM
+// speed; a counting pre-pass would read the text twice.  So K0 speculates and verifies:
+//
+//   k0_parse_spec   no dependency between tiles.  Per 16 KiB tile: (1) coalesced 128-bit loads bring
+//                   the tile plus a 1 KiB halo (the bytes before it) into shared memory, '\n' masks of
+//                   the 16-byte units computed on the way (SIMD byte compare); (2) one block scan ranks
+//                   the tile's newlines and every newline drops the start of the following line into a
+//                   shared-memory list (the halo contributes its last four); (3) the tile CLAIMS its
+//                   phase: the first of its first four newlines that ends a well-formed record ('@' and
+//                   '+' in place, sequence and quality equally long); (4) one thread per record whose
+//                   quality line ends in the tile packs it straight out of shared memory -- aligned
+//                   32-bit loads realigned by funnel shift, four bases per step (2-bit codes and
+//                   non-ACGT flags on all four bytes at once), quality_trim_index on both ends, format
+//                   checks -> bases / nmask / meta; output slots come from one atomic per tile (K1
+//                   does not care about record order).
+//   k0_verify       one small CTA: exclusive scan of the tiles' newline counts -> the true phase of
+//                   every tile; all claims right -> the launch stands (line count carried on, error
+//                   flags committed); any claim wrong or undecided (pathological or malformed text,
+//                   records longer than the halo at a tile start) -> the region is parsed again by
+//   k0_parse_pack   the exact path: the same tile code behind a chained scan with warp-wide decoupled
+//                   look-back, seeded with the line count carried over from the previous launch.  It is
+//                   launched after every k0_verify and returns at once unless asked for.
 // Records longer than the halo (kilobyte headers) take a byte-wise path through global memory; tiles
 // with more newlines than the list holds (reads of a few bases) are processed in several passes.
 #pragma once
@@ -46,7 +57,12 @@ struct K0Params {
 struct K0State {
     u64 lines[2];       // newlines of the chunk before the region
     u64 nrec;           // records packed by the last launch (K1 reads it)
+    u32 err_spec;       // format flags raised by the speculative launch (committed by k0_verify)
+    u32 need_exact;     // k0_verify: the speculation failed, k0_parse_pack has to redo the region
 };
+
+#define K0_CLAIM_NONE 4u        // none of the tile's (fewer than four) newlines ends a record
+#define K0_CLAIM_UNDECIDED 5u   // a candidate could not be tested inside the halo
 
 __device__ __forceinline__ u32 nl_mask_words(u32 x, u32 y, u32 z, u32 w)
 {
@@ -138,26 +154,265 @@ __device__ __forceinline__ void k0_pack_record(F32 ld32, F8 ld8, u32 a0, u32 a1,
     meta = (u32)sl | ((u32)start << 8) | ((u32)stop << 16);
 }
 
+
+// ---- tile building blocks shared by the speculative and the exact kernel -------------------------
+
+// 1. halo + tile into shared memory, newline mask per 16-byte unit.  Bytes at or beyond reg_end are not
+// touched (the next region may not have landed yet); vnl puts a virtual newline at byte reg_end.
+__device__ __forceinline__ void k0_load_tile(const unsigned char *__restrict__ text, i64 halo_start, u64 reg_end, int vnl,
+                                             unsigned char *buf, u16 *m16)
+{
+    for (int u = threadIdx.x; u < K0_UNITS; u += K0_THREADS) {
+        const i64 g0 = halo_start + 16 * (i64)u;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        u32 m = 0;
+        if (g0 >= 0 && (u64)g0 < reg_end) {
+            if ((u64)g0 + 16 <= reg_end) {
+                v = __ldg(reinterpret_cast<const uint4 *>(text + g0));
+            } else {                                     // the chunk's last, partial unit: byte loads only
+                u32 w4[4] = {0, 0, 0, 0};
+                for (int b = 0; (u64)g0 + b < reg_end; b++) w4[b >> 2] |= (u32)text[g0 + b] << ((b & 3) * 8);
+                v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+            m = nl_mask_words(v.x, v.y, v.z, v.w);
+            const u64 rem = reg_end - (u64)g0;
+            if (rem < 16) m &= (1u << rem) - 1u;
+        }
+        if (vnl && g0 <= (i64)reg_end && (i64)reg_end < g0 + 16) m |= 1u << (u32)((i64)reg_end - g0);
+        *reinterpret_cast<uint4 *>(buf + 16 * u) = v;
+        m16[u] = (u16)m;
+    }
+}
+
+// 3. line-start list of one pass: entry o + 4 - pass_lo = shared offset of the line that follows the
+// tile's o-th newline; in pass 0 entries 0..3 come from the halo's last four newlines.
+__device__ __forceinline__ void k0_fill_list(u32 pass_lo, u32 ex, const u32 *mw, u64 tile_start, const u16 *m16, u16 *lst)
+{
+    const unsigned tid = threadIdx.x;
+    u32 o = ex;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u32 m = mw[k];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const u32 li = o + 4 - pass_lo;
+            if (li < K0_CAP) lst[li] = (u16)(K0_HALO + 128 * tid + 32 * k + b + 1);
+            o++;
+        }
+    }
+    if (pass_lo == 0 && tid == 32) {
+        int found = 0;
+        if (tile_start == 0) { lst[3] = (u16)K0_HALO; found = 1; }     // the chunk's first line
+        else {
+            for (int u = K0_HALO / 16 - 1; u >= 0 && found < 4; u--) {
+                u32 m = m16[u];
+                while (m && found < 4) {
+                    const int b = 31 - __clz(m);
+                    m &= ~(1u << b);
+                    lst[3 - found] = (u16)(16 * u + b + 1);
+                    found++;
+                }
+            }
+        }
+        for (; found < 4; found++) lst[3 - found] = K0_NONE;
+    }
+}
+
+// 4. the records whose terminating newline has ordinal o in [pass_lo, pass_lo + K0_CAP - 4) and
+// o = o0 (mod 4): record with ordinal o goes to slot slot0 + (o - o0) / 4.
+template <int W>
+__device__ __forceinline__ void k0_pack_pass(const unsigned char *__restrict__ text, u64 reg_end, i64 delta, const unsigned char *buf,
+                                             const u16 *lst, u32 pass_lo, u32 o0, u32 T, u64 slot0, u64 rec_cap, const K0Params &prm,
+                                             u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta, u32 *err_word)
+{
+    constexpr int NW = W / 2;
+    const unsigned tid = threadIdx.x;
+    const u32 lo = pass_lo > o0 ? pass_lo + ((o0 + 4 - (pass_lo & 3)) & 3) : o0;
+    u32 hi = pass_lo + K0_CAP - 4;
+    if (hi > T) hi = T;
+    for (u32 o = lo + 4 * tid; o < hi; o += 4 * K0_THREADS) {
+        const u64 slot = slot0 + ((o - o0) >> 2);
+        const u32 li = o + 4 - pass_lo;
+        u32 l[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) l[k] = lst[li - 4 + k];
+        u64 s[W], nm[NW];
+        u32 mt, bad;
+        if (l[0] != K0_NONE) {
+            const unsigned char *b0 = buf;
+            auto ld32 = [b0](u32 off) { return *reinterpret_cast<const u32 *>(b0 + off); };
+            auto ld8 = [b0](u32 off) { return (u32)b0[off]; };
+            k0_pack_record<W>(ld32, ld8, l[0], l[1], l[2], l[3], l[4], prm, s, nm, mt, bad);
+        } else {
+            // a line of this record starts before the halo: find the missing starts in global memory
+            u64 g[5];
+            g[4] = (u64)((i64)l[4] + delta);
+            for (int k = 3; k >= 0; k--) {
+                if (l[k] != K0_NONE) { g[k] = (u64)((i64)l[k] + delta); continue; }
+                u64 p = g[k + 1] - 1;                // the newline that ends line k
+                while (p > 0 && text[p - 1] != '\n') p--;
+                g[k] = p;
+            }
+            const u64 gb = g[0] & ~3ull;
+            const unsigned char *tb = text + gb;
+            const u64 lim = reg_end;
+            auto ld8 = [tb, gb, lim](u32 off) { return gb + off < lim ? (u32)tb[off] : 0u; };
+            auto ld32 = [ld8](u32 off) { return ld8(off) | (ld8(off + 1) << 8) | (ld8(off + 2) << 16) | (ld8(off + 3) << 24); };
+            if (g[4] - gb >= 0xFFFFFF00ull) {
+                bad = ERRF_FORMAT; mt = 0;
+#pragma unroll
+                for (int w = 0; w < W; w++) s[w] = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) nm[w] = 0;
+            } else {
+                k0_pack_record<W>(ld32, ld8, (u32)(g[0] - gb), (u32)(g[1] - gb), (u32)(g[2] - gb), (u32)(g[3] - gb), (u32)(g[4] - gb),
+                                  prm, s, nm, mt, bad);
+            }
+        }
+        if (bad) atomicOr(err_word, bad);
+        if (slot < rec_cap) {
+            if (W == 2) *reinterpret_cast<ulonglong2 *>(bases + slot * 2) = make_ulonglong2(s[0], s[1]);
+            else {
+#pragma unroll
+                for (int w = 0; w < W; w++) bases[slot * W + w] = s[w];
+            }
+#pragma unroll
+            for (int w = 0; w < NW; w++) nmask[slot * NW + w] = nm[w];
+            meta[slot] = mt;
+        } else atomicOr(err_word, ERRF_FORMAT);
+    }
+}
+
+// Does the tile's newline with list index li end a well-formed record?  (first-record test of the claim)
+__device__ __forceinline__ u32 k0_test_candidate(const unsigned char *buf, const u16 *lst, u32 li)
+{
+    u32 l[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) l[k] = lst[li - 4 + k];
+    if (l[0] == K0_NONE) return 2u;                  // cannot tell inside the halo
+    if (buf[l[0]] != '@' || buf[l[2]] != '+') return 0u;
+    int sl = (int)(l[2] - 1 - l[1]), ql = (int)(l[4] - 1 - l[3]);
+    while (sl > 0 && buf[l[1] + sl - 1] == '\r') sl--;
+    while (ql > 0 && buf[l[3] + ql - 1] == '\r') ql--;
+    return sl == ql ? 1u : 0u;
+}
+
 // text: start of the chunk; the launch covers bytes [reg_start, reg_end) of it (reg_start a multiple
 // of K0_TILE); vnl: the chunk's last line has no '\n' -- a virtual one sits at byte reg_end (last
-// region only).  ctl[0] = tile ticket, ctl[1 + t] = status of tile t (zeroed before the launch).
-// par: which K0State::lines slot holds the count carried in.  Record r of the chunk (lines 4r..4r+3)
-// goes to slot r - (lines_in >> 2) of the output arrays.  last_region: the chunk ends with this
-// launch, so the line count must be a multiple of four.
+// region only).  info[t] = newline count of tile t | claim << 20.  state->nrec and state->err_spec
+// are zeroed before the launch.
+template <int W>
+__global__ void __launch_bounds__(K0_THREADS)
+k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end, int vnl, u32 ntiles,
+              u32 *__restrict__ info, K0State *__restrict__ state, K0Params prm, u64 rec_cap,
+              u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta)
+{
+    __shared__ __align__(16) unsigned char buf[K0_HALO + K0_TILE + 16];
+    __shared__ __align__(16) u16 m16[K0_UNITS + 8];
+    __shared__ u16 lst[K0_CAP];
+    __shared__ u32 sh_scan[33];
+    __shared__ u32 sh_claim;
+    __shared__ u64 sh_slot0;
+    const unsigned tid = threadIdx.x;
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u64 tile_start = reg_start + (u64)tile * K0_TILE;
+        const i64 halo_start = (i64)tile_start - K0_HALO;
+        k0_load_tile(text, halo_start, reg_end, vnl, buf, m16);
+        __syncthreads();
+        const uint4 mm = *reinterpret_cast<const uint4 *>(m16 + K0_HALO / 16 + 8 * tid);   // this thread's 128 bytes
+        const u32 mw[4] = {mm.x, mm.y, mm.z, mm.w};
+        const u32 cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
+        u32 T;
+        const u32 ex = block_excl_scan(cnt, sh_scan, &T);
+        u32 o0 = K0_CLAIM_NONE;
+        u64 slot0 = 0;
+        for (u32 pass_lo = 0; pass_lo == 0 || pass_lo < T; pass_lo += K0_CAP - 4) {
+            k0_fill_list(pass_lo, ex, mw, tile_start, m16, lst);
+            __syncthreads();
+            if (pass_lo == 0) {
+                if (tid < 32) {                              // the claim: first of the first four newlines that ends a record
+                    const u32 r = (tid < 4 && tid < T) ? k0_test_candidate(buf, lst, tid + 4) : 0u;
+                    const unsigned okm = __ballot_sync(0xffffffffu, r == 1u), unk = __ballot_sync(0xffffffffu, r == 2u);
+                    u32 claim = okm ? (u32)(__ffs(okm) - 1) : K0_CLAIM_NONE;
+                    if (unk && (!okm || (u32)(__ffs(unk) - 1) < claim)) claim = K0_CLAIM_UNDECIDED;
+                    if (tid == 0) {
+                        const u32 nrec = (claim < 4 && T > claim) ? (T - claim + 3) / 4 : 0u;
+                        sh_claim = claim;
+                        sh_slot0 = nrec ? atomicAdd(&state->nrec, (u64)nrec) : 0ull;
+                        info[tile] = T | (claim << 20);
+                    }
+                }
+                __syncthreads();
+                o0 = sh_claim; slot0 = sh_slot0;
+            }
+            if (o0 < 4)
+                k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, slot0, rec_cap, prm, bases, nmask, meta, &state->err_spec);
+            __syncthreads();
+        }
+    }
+}
+
+// True phase of every tile from the exclusive scan of the newline counts; commits or rejects the
+// speculative launch.  One CTA.
+__global__ void __launch_bounds__(1024)
+k0_verify(const u32 *__restrict__ info, u32 ntiles, K0State *__restrict__ state, int par, int last_region,
+          u32 *__restrict__ err_flags, u64 *__restrict__ processed)
+{
+    __shared__ u32 sh_scan[33];
+    const u64 lines_in = state->lines[par];
+    u64 carry = 0;
+    int bad = 0;
+    constexpr u32 ITEMS = 16;                                        // consecutive tiles per thread and round
+    for (u32 base = 0; base < ntiles; base += 1024 * ITEMS) {
+        const u32 t0 = base + threadIdx.x * ITEMS;
+        u32 v[ITEMS], sum = 0;
+#pragma unroll
+        for (u32 k = 0; k < ITEMS; k++) { v[k] = (t0 + k < ntiles) ? info[t0 + k] : 0u; sum += v[k] & 0xFFFFFu; }
+        u32 total;
+        u64 G = lines_in + carry + block_excl_scan(sum, sh_scan, &total);
+#pragma unroll
+        for (u32 k = 0; k < ITEMS; k++) {
+            const u32 T = v[k] & 0xFFFFFu, claim = v[k] >> 20;
+            const u32 o0 = (u32)((3ull - (G & 3ull)) & 3ull);
+            const u32 expect = o0 < T ? o0 : K0_CLAIM_NONE;
+            if (t0 + k < ntiles && claim != expect) bad = 1;
+            G += T;
+        }
+        carry += total;
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) {
+        if (bad) state->need_exact = 1u;
+        else {
+            const u64 lines_out = lines_in + carry;
+            state->need_exact = 0u;
+            state->lines[par ^ 1] = lines_out;
+            if (state->err_spec) atomicOr(err_flags, state->err_spec);
+            atomicAdd(processed, state->nrec);
+            if (last_region && (lines_out & 3ull)) atomicOr(err_flags, ERRF_PARTIAL);
+        }
+    }
+}
+
+// The exact path (runs only when k0_verify asks for it).  ctl[0] = tile ticket, ctl[1 + t] = status of
+// tile t (zeroed before the launch).  par: which K0State::lines slot holds the count carried in.
+// Record r of the chunk (lines 4r..4r+3) goes to slot r - (lines_in >> 2) of the output arrays.
+// last_region: the chunk ends with this launch, so the line count must be a multiple of four.
 template <int W>
 __global__ void __launch_bounds__(K0_THREADS)
 k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end, int vnl, int last_region, u32 ntiles,
               u64 *__restrict__ ctl, K0State *__restrict__ state, int par, K0Params prm, u64 rec_cap,
               u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta, u32 *__restrict__ err_flags,
-              u64 *__restrict__ processed)
+              u64 *__restrict__ processed, int always)
 {
-    constexpr int NW = W / 2;
     __shared__ __align__(16) unsigned char buf[K0_HALO + K0_TILE + 16];
     __shared__ __align__(16) u16 m16[K0_UNITS + 8];
     __shared__ u16 lst[K0_CAP];
     __shared__ u32 sh_scan[33];
     __shared__ u32 sh_tile;
     __shared__ u64 sh_excl;
+    if (!always && !state->need_exact) return;
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const u64 lines_in = state->lines[par];
     const u64 rec0 = lines_in >> 2;
@@ -169,29 +424,9 @@ k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
         if (tile >= ntiles) break;
         const u64 tile_start = reg_start + (u64)tile * K0_TILE;
         const i64 halo_start = (i64)tile_start - K0_HALO;
-        // ---- 1. load halo + tile, newline masks
-        for (int u = tid; u < K0_UNITS; u += K0_THREADS) {
-            const i64 g0 = halo_start + 16 * (i64)u;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            u32 m = 0;
-            if (g0 >= 0 && (u64)g0 < reg_end) {
-                if ((u64)g0 + 16 <= reg_end) {
-                    v = __ldg(reinterpret_cast<const uint4 *>(text + g0));
-                } else {                                     // the chunk's last, partial unit: byte loads only
-                    u32 w4[4] = {0, 0, 0, 0};
-                    for (int b = 0; (u64)g0 + b < reg_end; b++) w4[b >> 2] |= (u32)text[g0 + b] << ((b & 3) * 8);
-                    v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                }
-                m = nl_mask_words(v.x, v.y, v.z, v.w);
-                const u64 rem = reg_end - (u64)g0;
-                if (rem < 16) m &= (1u << rem) - 1u;
-            }
-            if (vnl && g0 <= (i64)reg_end && (i64)reg_end < g0 + 16) m |= 1u << (u32)((i64)reg_end - g0);
-            *reinterpret_cast<uint4 *>(buf + 16 * u) = v;
-            m16[u] = (u16)m;
-        }
+        k0_load_tile(text, halo_start, reg_end, vnl, buf, m16);
         __syncthreads();
-        // ---- 2. rank the tile's newlines; chained scan over the tiles
+        // rank the tile's newlines; chained scan over the tiles
         const uint4 mm = *reinterpret_cast<const uint4 *>(m16 + K0_HALO / 16 + 8 * tid);   // this thread's 128 bytes
         const u32 mw[4] = {mm.x, mm.y, mm.z, mm.w};
         const u32 cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
@@ -210,7 +445,7 @@ k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
                     const unsigned im = __ballot_sync(0xffffffffu, (s >> 62) == 0ull);
                     const int fp = pm ? __ffs(pm) - 1 : 32;
                     const unsigned need = fp < 31 ? ((2u << fp) - 1u) : 0xffffffffu;
-                    if (im & need) continue;                 // a tile in the window has not published yet
+                    if (im & need) { __nanosleep(200); continue; }                     // a tile in the window has not published yet
                     u64 val = ((int)lane <= fp) ? (s & K0_ST_VAL) : 0ull;
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
@@ -224,89 +459,12 @@ k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
                 sh_excl = excl;
             }
         }
-        // ---- 3 + 4. line-start list, then the records that end in this tile
-        const i64 delta = halo_start;                        // global offset = shared offset + delta
         for (u32 pass_lo = 0; pass_lo == 0 || pass_lo < T; pass_lo += K0_CAP - 4) {
-            {
-                u32 o = ex;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    u32 m = mw[k];
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1;
-                        const u32 li = o + 4 - pass_lo;
-                        if (li < K0_CAP) lst[li] = (u16)(K0_HALO + 128 * tid + 32 * k + b + 1);
-                        o++;
-                    }
-                }
-            }
-            if (pass_lo == 0 && tid == 32) {                 // the halo's last four newlines (warp 1 while warp 0 looks back)
-                int found = 0;
-                if (tile_start == 0) { lst[3] = (u16)K0_HALO; found = 1; }     // the chunk's first line
-                else {
-                    for (int u = K0_HALO / 16 - 1; u >= 0 && found < 4; u--) {
-                        u32 m = m16[u];
-                        while (m && found < 4) {
-                            const int b = 31 - __clz(m);
-                            m &= ~(1u << b);
-                            lst[3 - found] = (u16)(16 * u + b + 1);
-                            found++;
-                        }
-                    }
-                }
-                for (; found < 4; found++) lst[3 - found] = K0_NONE;
-            }
+            k0_fill_list(pass_lo, ex, mw, tile_start, m16, lst);
             __syncthreads();
             const u64 G = sh_excl;
             const u32 o0 = (u32)((3ull - (G & 3ull)) & 3ull);        // first record-terminating newline of the tile
-            const u32 lo = pass_lo > o0 ? pass_lo + ((o0 + 4 - (pass_lo & 3)) & 3) : o0;
-            u32 hi = pass_lo + K0_CAP - 4;
-            if (hi > T) hi = T;
-            for (u32 o = lo + 4 * tid; o < hi; o += 4 * K0_THREADS) {
-                const u64 slot = ((G + o) >> 2) - rec0;
-                const u32 li = o + 4 - pass_lo;
-                u32 l[5];
-#pragma unroll
-                for (int k = 0; k < 5; k++) l[k] = lst[li - 4 + k];
-                u64 s[W], nm[NW];
-                u32 mt, bad;
-                if (l[0] != K0_NONE) {
-                    const unsigned char *b0 = buf;
-                    auto ld32 = [b0](u32 off) { return *reinterpret_cast<const u32 *>(b0 + off); };
-                    auto ld8 = [b0](u32 off) { return (u32)b0[off]; };
-                    k0_pack_record<W>(ld32, ld8, l[0], l[1], l[2], l[3], l[4], prm, s, nm, mt, bad);
-                } else {
-                    // a line of this record starts before the halo: find the missing starts in global memory
-                    u64 g[5];
-                    g[4] = (u64)((i64)l[4] + delta);
-                    for (int k = 3; k >= 0; k--) {
-                        if (l[k] != K0_NONE) { g[k] = (u64)((i64)l[k] + delta); continue; }
-                        u64 p = g[k + 1] - 1;                // the newline that ends line k
-                        while (p > 0 && text[p - 1] != '\n') p--;
-                        g[k] = p;
-                    }
-                    const u64 gb = g[0] & ~3ull;
-                    const unsigned char *tb = text + gb;
-                    const u64 lim = reg_end;
-                    auto ld8 = [tb, gb, lim](u32 off) { return gb + off < lim ? (u32)tb[off] : 0u; };
-                    auto ld32 = [ld8](u32 off) { return ld8(off) | (ld8(off + 1) << 8) | (ld8(off + 2) << 16) | (ld8(off + 3) << 24); };
-                    if (g[4] - gb >= 0xFFFFFF00ull) { bad = ERRF_FORMAT; mt = 0; for (int w = 0; w < W; w++) s[w] = 0; for (int w = 0; w < NW; w++) nm[w] = 0; }
-                    else k0_pack_record<W>(ld32, ld8, (u32)(g[0] - gb), (u32)(g[1] - gb), (u32)(g[2] - gb), (u32)(g[3] - gb), (u32)(g[4] - gb),
-                                           prm, s, nm, mt, bad);
-                }
-                if (bad) atomicOr(err_flags, bad);
-                if (slot < rec_cap) {
-                    if (W == 2) *reinterpret_cast<ulonglong2 *>(bases + slot * 2) = make_ulonglong2(s[0], s[1]);
-                    else {
-#pragma unroll
-                        for (int w = 0; w < W; w++) bases[slot * W + w] = s[w];
-                    }
-#pragma unroll
-                    for (int w = 0; w < NW; w++) nmask[slot * NW + w] = nm[w];
-                    meta[slot] = mt;
-                } else atomicOr(err_flags, ERRF_FORMAT);
-            }
+            k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, ((G + o0) >> 2) - rec0, rec_cap, prm, bases, nmask, meta, err_flags);
             __syncthreads();
         }
         if (tile == ntiles - 1 && tid == 0) {                // hand the line count on to the next launch

@@ -310,8 +310,9 @@ __host__ __device__ __forceinline__ bool match_back(const PSeq<W> &p, int n, con
     return locate_back<W>(p, n, tp.aw[a], m, tp.error_rate, tp.min_overlap, rstart, matches);
 }
 
-// Insert exchange records (multi-GPU): record = W + W/2 u64 words, then
-// u32 len, then S u32 counts, padded to 8 bytes.
+// Exchange records (multi-GPU): W + W/2 u64 key words, then u32 (len | sample << 8), then the u32
+// read count of that sample -- 32 bytes at W = 2, one DRAM sector.  A sequence seen in k samples of the
+// sending rank travels as k records.
 template <int W>
 __global__ void __launch_bounds__(128)
 k1_import_records(const unsigned char *__restrict__ buf, u64 n_records, int rec_bytes, TableView<W> T)
@@ -324,58 +325,87 @@ k1_import_records(const unsigned char *__restrict__ buf, u64 n_records, int rec_
         for (int w = 0; w < W; w++) p.s[w] = 0;
 #pragma unroll
         for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
-        const u32 *c = nullptr;
-        int len = 0;
+        int len = 0, smp = 0;
+        u32 c = 0;
         if (on) {
             const u64 *q = reinterpret_cast<const u64 *>(buf + r * (u64)rec_bytes);
+            if (W == 2) {
+                const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(q), b = *reinterpret_cast<const ulonglong2 *>(q + 2);
+                p.s[0] = a.x; p.s[1] = a.y; p.nm[0] = b.x;
+                len = (int)(b.y & 0xFFull); smp = (int)((b.y >> 8) & 0xFFFFFFull); c = (u32)(b.y >> 32);
+            } else {
 #pragma unroll
-            for (int w = 0; w < W; w++) p.s[w] = q[w];
+                for (int w = 0; w < W; w++) p.s[w] = q[w];
 #pragma unroll
-            for (int w = 0; w < W / 2; w++) p.nm[w] = q[W + w];
-            c = reinterpret_cast<const u32 *>(q + W + W / 2);
-            len = (int)c[0];
+                for (int w = 0; w < W / 2; w++) p.nm[w] = q[W + w];
+                const u64 t = q[W + W / 2];
+                len = (int)(t & 0xFFull); smp = (int)((t >> 8) & 0xFFFFFFull); c = (u32)(t >> 32);
+            }
         }
-        // records of one sender are distinct; the same key arrives from several senders in different warps
+        // records of one sender and sample are distinct; the same key arrives from several senders / samples
         bool lead; u32 id, cnt;
         table_find_warp<W, false>(T, p, len, on, on ? pseq_hash<W>(p, len) : 0ull, lead, id, cnt);
-        if (lead)
-            for (int s = 0; s < T.S; s++) if (c[1 + s]) atomicAdd(&T.counts[(u64)id * T.S + s], c[1 + s]);
+        if (lead && c && smp < T.S) atomicAdd(&T.counts[(u64)id * T.S + smp], c);
     }
 }
 
-// Write every unique as an exchange record, grouped by owner = hash % n_parts.
-// Pass 1 (count_only) fills part_counts; after an exclusive scan into
-// part_cursor, pass 2 scatters.
+// Write every (unique, sample) pair with a non-zero count as an exchange record, grouped by owner =
+// hash % n_parts.  Pass 1 (count_only) fills part_counts; after an exclusive scan into part_cursor,
+// pass 2 scatters.  The number of uniques is read on the device (no host round trip).
 template <int W>
 __global__ void __launch_bounds__(128)
-k1_export_records(TableView<W> T, u64 n_unique, int n_parts, int rec_bytes, int count_only,
+k1_export_records(TableView<W> T, int n_parts, int rec_bytes, int count_only, u64 cap_records,
                   u64 *__restrict__ part_counts, u64 *__restrict__ part_cursor, unsigned char *__restrict__ out)
 {
-    for (u64 id = (u64)blockIdx.x * blockDim.x + threadIdx.x; id < n_unique; id += (u64)gridDim.x * blockDim.x) {
+    u64 n_unique = *T.n_unique;
+    if (n_unique > T.max_unique) n_unique = T.max_unique;
+    const int lane = threadIdx.x & 31;
+    for (u64 id0 = (u64)blockIdx.x * blockDim.x; id0 < n_unique; id0 += (u64)gridDim.x * blockDim.x) {
+        const u64 id = id0 + threadIdx.x;
+        const bool on = id < n_unique;
         u64 s[W], nm[W / 2];
+        int len = 0, part = -1;
+        if (on) {
 #pragma unroll
-        for (int w = 0; w < W; w++) s[w] = T.useq[id * W + w];
+            for (int w = 0; w < W; w++) s[w] = T.useq[id * W + w];
 #pragma unroll
-        for (int w = 0; w < W / 2; w++) nm[w] = T.unmask[id * (W / 2) + w];
-        const int len = T.ulen[id];
-        const u64 h = key_hash_words(s, W, nm, len);
-        const int part = (int)(owner_hash(h) % (u64)n_parts);
-        // few destinations, many records: lanes bound for the same rank share one atomic
-        const unsigned peers = __match_any_sync(__activemask(), part);
-        const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-        const u32 rank = __popc(peers & ((1u << lane) - 1u));
-        if (count_only) { if (lane == leader) atomicAdd(&part_counts[part], (u64)__popc(peers)); continue; }
-        u64 dst = 0;
-        if (lane == leader) dst = atomicAdd(&part_cursor[part], (u64)__popc(peers));
-        dst = __shfl_sync(peers, dst, leader) + rank;
-        u64 *q = reinterpret_cast<u64 *>(out + dst * (u64)rec_bytes);
+            for (int w = 0; w < W / 2; w++) nm[w] = T.unmask[id * (W / 2) + w];
+            len = T.ulen[id];
+            part = (int)(owner_hash(key_hash_words(s, W, nm, len)) % (u64)n_parts);
+        }
+        for (int x = 0; x < T.S; x++) {                      // warp-uniform trip count
+            const u32 c = on ? T.counts[id * T.S + x] : 0u;
+            // few destinations, many records: lanes bound for the same rank share one atomic
+            const unsigned peers = __match_any_sync(0xffffffffu, c ? part : -1 - lane);
+            if (!c) continue;
+            const int leader = __ffs(peers) - 1;
+            const u32 rank = __popc(peers & ((1u << lane) - 1u));
+            if (count_only) { if (lane == leader) atomicAdd(&part_counts[part], (u64)__popc(peers)); continue; }
+            u64 dst = 0;
+            if (lane == leader) dst = atomicAdd(&part_cursor[part], (u64)__popc(peers));
+            dst = __shfl_sync(peers, dst, leader) + rank;
+            if (dst >= cap_records) { atomicOr(T.err, ERRF_FULL); continue; }
+            u64 *q = reinterpret_cast<u64 *>(out + dst * (u64)rec_bytes);
+            const u64 tail = (u64)len | ((u64)x << 8) | ((u64)c << 32);
+            if (W == 2) {
+                *reinterpret_cast<ulonglong2 *>(q) = make_ulonglong2(s[0], s[1]);
+                *reinterpret_cast<ulonglong2 *>(q + 2) = make_ulonglong2(nm[0], tail);
+            } else {
 #pragma unroll
-        for (int w = 0; w < W; w++) q[w] = s[w];
+                for (int w = 0; w < W; w++) q[w] = s[w];
 #pragma unroll
-        for (int w = 0; w < W / 2; w++) q[W + w] = nm[w];
-        u32 *c = reinterpret_cast<u32 *>(q + W + W / 2);
-        c[0] = (u32)len;
-        for (int x = 0; x < T.S; x++) c[1 + x] = T.counts[id * T.S + x];
-        if (((1 + T.S) & 1)) c[1 + T.S] = 0;
+                for (int w = 0; w < W / 2; w++) q[W + w] = nm[w];
+                q[W + W / 2] = tail;
+            }
+        }
     }
+}
+
+// counts[id][*] = 0 for the ids in use (cheaper than a memset of the whole array when S is large)
+__global__ void k1_clear_counts(u32 *__restrict__ counts, const u64 *__restrict__ n_unique_ptr, u64 max_unique, int S)
+{
+    u64 n = *n_unique_ptr;
+    if (n > max_unique) n = max_unique;
+    n *= (u64)S;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) counts[i] = 0;
 }

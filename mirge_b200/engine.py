@@ -28,6 +28,7 @@ class Engine:
         self.S = int(n_samples)
         self.spike_in = bool(spike_in)
         self.max_read_len = 64 if max_read_len <= 64 else 128
+        self.max_unique = int(max_unique)
         self.h = _capi.ctx_p()
         rc = lib.mirge_create(device, self.S, int(self.spike_in), int(max_unique), int(max_read_len), C.byref(self.h))
         if rc:
@@ -156,10 +157,27 @@ class Engine:
     def record_bytes(self):
         return int(lib.mirge_record_bytes(self.h))
 
-    def export_records_device(self, n_parts, dev_ptr, cap_records):
-        pc = np.zeros(n_parts, np.uint64)
-        self._ck(lib.mirge_export_records_device(self.h, n_parts, C.c_void_p(int(dev_ptr)), int(cap_records), _ptr(pc)))
-        return pc
+    def export_records_device(self, n_parts, dev_ptr, cap_records, counts_dev_ptr=None):
+        """Records grouped by owner into dev_ptr.  With counts_dev_ptr (device int64[n_parts]) the call is fully
+        asynchronous and returns None; without it the group sizes are fetched (synchronises) and returned."""
+        if counts_dev_ptr is not None:
+            self._ck(lib.mirge_export_records_device(self.h, n_parts, C.c_void_p(int(dev_ptr)), int(cap_records), C.c_void_p(int(counts_dev_ptr))))
+            return None
+        import torch
+        pc = torch.empty(n_parts, dtype=torch.int64, device='cuda')
+        torch.cuda.synchronize()         # the engine may run on a stream of its own
+        self._ck(lib.mirge_export_records_device(self.h, n_parts, C.c_void_p(int(dev_ptr)), int(cap_records), C.c_void_p(pc.data_ptr())))
+        self.sync()
+        return pc.cpu().numpy().astype(np.uint64)
+
+    def tables_words(self):
+        return int(lib.mirge_tables_words(self.h))
+
+    def pack_tables_device(self, dev_ptr):
+        self._ck(lib.mirge_pack_tables_device(self.h, C.c_void_p(int(dev_ptr))))
+
+    def unpack_tables_device(self, dev_ptr):
+        self._ck(lib.mirge_unpack_tables_device(self.h, C.c_void_p(int(dev_ptr))))
 
     def reset(self):
         self._ck(lib.mirge_reset(self.h))

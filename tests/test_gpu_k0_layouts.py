@@ -1,7 +1,9 @@
 """K0 (single-pass FASTQ parse + pack, csrc/k0_parse.cuh) against the oracle on text layouts that stress the tiling:
 records straddling 16 KiB tiles and feed regions, header lines longer than the 1 KiB halo (global-memory path), reads
 of a few bases (more newlines per tile than one pass of the line list holds), CRLF, a missing final newline, chunk
-lengths around multiples of the tile size, several chunks per sample."""
+lengths around multiples of the tile size, several chunks per sample.  Every layout runs through the speculative kernel
+(k0_parse_spec + k0_verify, falling back to the exact kernel when a tile cannot prove its line phase) and through the
+exact chained-scan kernel alone."""
 import numpy as np
 import pytest
 
@@ -10,11 +12,21 @@ from conftest import ILLUMINA
 pytestmark = pytest.mark.gpu
 
 
-def _collapse(O, fq_chunks, adapter=ILLUMINA, max_read_len=64, device_resident=False):
+def _collapse(O, fq_chunks, adapter=ILLUMINA, max_read_len=64, device_resident=False, exact_too=True):
+    """Runs the default path (speculate + verify, exact fallback when needed) and, with exact_too, the exact chained
+    path alone (mirge_debug bit 0x2000)."""
+    got = _collapse_mode(O, fq_chunks, adapter, max_read_len, device_resident, 0)
+    if exact_too:
+        assert _collapse_mode(O, fq_chunks, adapter, max_read_len, device_resident, 0x2000) == got
+    return got
+
+
+def _collapse_mode(O, fq_chunks, adapter, max_read_len, device_resident, mode):
     from mirge_b200.engine import Engine
     o = O.Oracle(1, False, adapter)
     e = Engine(1, False, 1 << 18, max_read_len)
     e.set_adapter(adapter)
+    e.set_trim_mode(mode)
     keep = []
     for fq in fq_chunks:
         if len(fq):
@@ -28,7 +40,10 @@ def _collapse(O, fq_chunks, adapter=ILLUMINA, max_read_len=64, device_resident=F
             e.feed_fastq(0, fq, 33)
     e.sync()
     oe, ee = o.export(), e.export_unique()
-    want = {s: int(c[0]) for s, c in zip(oe['seqs'], oe['counts'])}
+    want = {}
+    for s, c in zip(oe['seqs'], oe['counts']):       # the packed form turns every non-ACGT byte into N
+        key = ''.join(ch if ch in 'ACGT' else 'N' for ch in s.upper())
+        want[key] = want.get(key, 0) + int(c[0])
     got = {s.decode(): int(c[0]) for s, c in zip(ee['seq'], ee['counts'])}
     assert got == want
     op, ok = o.stats()
@@ -134,3 +149,16 @@ def test_partial_record_is_reported(oracle_mod):
         e.feed_fastq(0, fq[:cut + 1], 33)
         e.sync()
     assert ei.value.code == -3
+
+
+def test_speculation_is_rejected_on_ambiguous_text(oracle_mod):
+    """Quality lines that look like headers ('@' first) and sequence lines that look like '+' lines make the local
+    phase test ambiguous or wrong; k0_verify must notice and the exact path must give the reference's parse."""
+    rng = np.random.default_rng(17)
+    reads = _reads(rng, 3000, 16, 50)
+    # quality strings starting with '@' (a legal quality character, Q31): every quality line looks like a header
+    fq = _fastq(reads, qual=lambda r, k: '@' + 'I' * (len(r) - 1))
+    _collapse(oracle_mod, [fq])
+    # header-like quality AND a '+'-like sequence line in the same record (non-ACGT bytes collapse to N)
+    fq2 = _fastq(['+' + r[1:] for r in reads], qual=lambda r, k: '@' + 'I' * (len(r) - 1))
+    _collapse(oracle_mod, [fq2], adapter='none')

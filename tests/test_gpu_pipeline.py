@@ -121,10 +121,14 @@ def test_exchange_records_round_trip(small_world):
     u0 = e.export_unique()
     before = dict(zip(u0['seq'].tolist(), map(tuple, u0['counts'].tolist())))
     U, rb = len(u0['seq']), e.record_bytes()
-    buf = torch.empty(U * rb, dtype=torch.uint8, device='cuda')
-    pc = e.export_records_device(3, buf.data_ptr(), U)
-    assert int(pc.sum()) == U
-    own = np.bincount([owner_of(s, 3) for s in u0['seq'].tolist()], minlength=3)
+    n_rec = int((u0['counts'] > 0).sum())                         # one record per (sequence, sample) with reads
+    assert rb == 32
+    buf = torch.empty(n_rec * rb, dtype=torch.uint8, device='cuda')
+    pc = e.export_records_device(3, buf.data_ptr(), n_rec)
+    assert int(pc.sum()) == n_rec and n_rec > U
+    own = np.zeros(3, np.int64)
+    for s, c in zip(u0['seq'].tolist(), u0['counts']):
+        own[owner_of(s, 3)] += int((c > 0).sum())
     assert own.tolist() == [int(x) for x in pc]                 # host hash == device hash
     e.reset_unique()
     off = 0
