@@ -35,7 +35,7 @@ enum {
 enum {
     MIRGE_LIB_MIRNA = 0, MIRGE_LIB_HAIRPIN = 1, MIRGE_LIB_MATURE_TRNA = 2, MIRGE_LIB_PRE_TRNA = 3,
     MIRGE_LIB_SNORNA = 4, MIRGE_LIB_RRNA = 5, MIRGE_LIB_NCRNA_OTHERS = 6, MIRGE_LIB_MRNA = 7,
-    MIRGE_LIB_SPIKEIN = 9, MIRGE_N_LIBS = 10
+    MIRGE_LIB_GENOME = 8, MIRGE_LIB_SPIKEIN = 9, MIRGE_N_LIBS = 10
 };
 
 #define MIRGE_N_ROUNDS 10       /* 9 rounds, 10 with -spikeIn */
@@ -103,6 +103,28 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
  * rounds in order over the still un-annotated unique sequences, including the
  * poly-T pre-tRNA round (:664-704). */
 int mirge_annotate(mirge_ctx *ctx);
+
+/* -- genome passes --------------------------------------- */
+
+/* index.Libs/<sp>_genome.*.ebwt (__main__.py:270): chromosomes concatenated as
+ * ASCII with offsets[n_refs+1]; builds the 2-bit genome and ONE prefix-ordered
+ * k-mer table that serves every seed length (csrc/k2_genome.cuh). */
+int mirge_load_genome(mirge_ctx *ctx, int n_refs, const char *seq_ascii, const uint64_t *offsets);
+/* `bowtie <genome> -n N|-v V -f -a [-3 trim3] [-l seedlen] [--norc]` for n reads
+ * (ASCII, `stride` bytes apart, lens[i] bases each; host memory):
+ *   utils/writeDataToCSV.py:1260  mode 0, param 1, seedlen 28, trim3 2   (A-to-I candidates)
+ *   utils/writeDataToCSV.py:1488  mode 0, param 0, seedlen 28, trim3 2
+ *   __main__.py:538               mode 0, param 0, seedlen 25, trim3 0   (-m 3 --best: caller suppresses sum > 3)
+ * counts[i*4 + k] (host) = number of alignments of read i, both strands unless
+ * norc, with k mismatches.  What bowtie would print per read follows from the
+ * counts (-a: all of them; --best --strata: the lowest occupied k; -m M:
+ * nothing when the sum exceeds M).  Synchronises. */
+int mirge_genome_pass(mirge_ctx *ctx, uint64_t n, const char *reads, int stride, const uint8_t *lens,
+                      int mode, int param, int seedlen, int trim3, int norc, uint32_t *counts);
+/* Same for unique sequences already in the device table, named by their ids
+ * (row numbers of mirge_export_unique). */
+int mirge_genome_pass_ids(mirge_ctx *ctx, uint64_t n, const uint32_t *ids, int mode, int param, int seedlen, int trim3, int norc,
+                          uint32_t *counts);
 
 /* -- stage 3: tallies ----------------------------------------------------- */
 

@@ -40,6 +40,9 @@ _SIGS = {
     'mirge_feed_fastq_device': (C.c_int, [ctx_p, C.c_int, vp, u64, C.c_int]),
     'mirge_get_stats': (C.c_int, [ctx_p, vp, vp, vp]),
     'mirge_load_library': (C.c_int, [ctx_p, C.c_int, C.c_int, vp, vp]),
+    'mirge_load_genome': (C.c_int, [ctx_p, C.c_int, vp, vp]),
+    'mirge_genome_pass': (C.c_int, [ctx_p, u64, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    'mirge_genome_pass_ids': (C.c_int, [ctx_p, u64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     'mirge_annotate': (C.c_int, [ctx_p]),
     'mirge_tally': (C.c_int, [ctx_p]),
     'mirge_export_unique': (C.c_int, [ctx_p, u64, C.c_int, vp, vp, vp, vp, vp, vp, vp]),

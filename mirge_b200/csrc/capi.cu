@@ -19,19 +19,20 @@
 #include "k1_trim.cuh"
 #include "k1_kernel.cuh"
 #include "k2_map.cuh"
+#include "k2_genome.cuh"
 #include "k3_tally.cuh"
 
 enum KernelId {
     KID_K0_COUNT = 0, KID_K0_SCAN, KID_K0_LINES,          // 0..2: retired (round 1's three-pass K0)
     KID_K0_PACK, KID_K1_TRIM, KID_K3_KEYS, KID_K3_SORT,
-    KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_RESET,
+    KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_RESET, KID_GENOME,
     KID_K2_ROUND0 = 16,   // .. KID_K2_ROUND0 + 9
     KID_K1_CLASSIFY = 26, KID_K1_SCAN, KID_K1_GENERAL, KID_K1_SLOW,
     KID_N = 30
 };
 static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
     "", "", "", "k0_parse_pack", "k1_trim_collapse", "k3_make_keys",
-    "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "reset_memset", "", "",
+    "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "reset_memset", "k2g_genome_all_hits", "",
     "k2_round0_mirna_exact", "k2_round1_hairpin", "k2_round2_mature_trna", "k2_round3_pre_trna", "k2_round4_snorna",
     "k2_round5_rrna", "k2_round6_ncrna_others", "k2_round7_mrna", "k2_round8_isomir", "k2_round9_spikein",
     "k1a_classify_collapse", "k1b_scan_class1", "k1c_general_search", "k1d_slow_search", "", ""};
@@ -45,6 +46,8 @@ struct DevLib {
     int tab_k[K2_MAX_TABS];
     u32 *tab_off[K2_MAX_TABS];
     u32 *tab_pos[K2_MAX_TABS];
+    u32 *gx_off = nullptr, *gx_pos = nullptr;     // genome slot: one prefix-ordered table for every seed length
+    int gx_kmax = 0;
 };
 
 struct ProfSpan { int kid; cudaEvent_t a, b; };
@@ -299,6 +302,7 @@ static void free_lib(DevLib &l)
 {
     cudaFree(l.seq); cudaFree(l.amb); cudaFree(l.ref_off); cudaFree(l.blk_ref);
     for (int t = 0; t < l.ntabs; t++) { cudaFree(l.tab_off[t]); cudaFree(l.tab_pos[t]); }
+    cudaFree(l.gx_off); cudaFree(l.gx_pos);
     l = DevLib();
 }
 
@@ -460,7 +464,7 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
     CK(ensure(&ctx->d_k0ctl, &ctx->k0ctl_cap, max_tiles + 2));
     CK(ensure(&ctx->d_k0info, &ctx->k0info_cap, max_tiles + 2));
     CK(cudaMemsetAsync(ctx->d_k0state, 0, sizeof(K0State), st));      // the chunk starts at line 0
-    const int k0_grid = wave_grid(k0_parse_pack<W>, K0_THREADS, ~0ull), k0s_grid = wave_grid(k0_parse_spec<W>, K0_THREADS, ~0ull);
+    const int k0_grid = wave_grid(k0_parse_pack<W>, K0_THREADS, 1ull << 40), k0s_grid = wave_grid(k0_parse_spec<W>, K0_THREADS, 1ull << 40);
     const bool exact_only = (ctx->force_slow & 0x2000) != 0;          // test hook: skip the speculation
     u32 *err_flags = (u32 *)(ctx->d_ctr + 1);
     u64 *processed = ctx->d_ctr + 5 + ctx->S + sample;
@@ -548,9 +552,9 @@ int mirge_get_stats(mirge_ctx *ctx, uint64_t *processed, uint64_t *kept, uint64_
 // ---------------------------------------------------------------------------
 // libraries
 // ---------------------------------------------------------------------------
-int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_ascii, const uint64_t *offsets)
+static int load_library_impl(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_ascii, const uint64_t *offsets)
 {
-    if (lib_id < 0 || lib_id >= MIRGE_N_LIBS || lib_id == 8 || n_refs < 0 || (n_refs > 0 && (!seq_ascii || !offsets)))
+    if (lib_id < 0 || lib_id >= MIRGE_N_LIBS || n_refs < 0 || (n_refs > 0 && (!seq_ascii || !offsets)))
         return fail(ctx, MIRGE_E_ARG, "mirge_load_library: bad argument");
     const u64 total = n_refs ? offsets[n_refs] : 0;
     if (total >= 0xFFFFFF00ull) return fail(ctx, MIRGE_E_ARG, "library larger than 4 Gbases is not supported");
@@ -586,13 +590,38 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
     CK(cudaMalloc(&d_ascii, total));
     CK(cudaMemcpyAsync(d_ascii, seq_ascii, total, cudaMemcpyHostToDevice, st));
     k2_pack_library<<<(unsigned)((nw64 + 127) / 128), 128, 0, st>>>(d_ascii, (u32)total, l.seq, l.amb);
+    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = n_refs; L.total = (u32)total;
+    if (lib_id == MIRGE_LIB_GENOME) {
+        // one prefix-ordered table: kmax-mers, first base most significant (k2_genome.cuh)
+        int kmax = 6;
+        while (kmax < 12 && (1ull << (2 * (kmax + 1))) <= 4 * total) kmax++;
+        const u64 nb = 1ull << (2 * kmax);
+        u32 *cursor = nullptr, *scratch = nullptr;
+        cudaError_t e = cudaMalloc(&l.gx_off, (nb + 1) * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMalloc(&cursor, (nb + 1) * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMalloc(&l.gx_pos, (total + 1) * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMalloc(&scratch, scan_scratch_elems(nb + 1) * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMemsetAsync(l.gx_off, 0, (nb + 1) * sizeof(u32), st);
+        if (e == cudaSuccess) {
+            const int grid = grid_for(total, 256, 148 * 8);
+            k2g_index_pass<<<grid, 256, 0, st>>>(L, kmax, 0, l.gx_off, nullptr);
+            device_excl_scan(l.gx_off, l.gx_off, nb + 1, scratch, st);
+            e = cudaMemcpyAsync(cursor, l.gx_off, (nb + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) k2g_index_pass<<<grid, 256, 0, st>>>(L, kmax, 1, cursor, l.gx_pos);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        cudaFree(cursor); cudaFree(scratch); cudaFree(d_ascii);
+        if (e != cudaSuccess) { ctx->err = std::string("genome index build failed: ") + cudaGetErrorString(e); return MIRGE_E_CUDA; }
+        l.gx_kmax = kmax;
+        CK(cudaGetLastError());
+        return MIRGE_OK;
+    }
     // seed tables: the miRNA library serves the 3-seed isomiR round on reads as
     // short as 13 nt (k = 4..8); the big mRNA library gets a 12-mer table.
     std::vector<int> ks;
     if (lib_id == MIRGE_LIB_MIRNA) ks = {4, 5, 6, 7, 8};
     else if (total >= (1u << 20)) ks = {8, 10, 12};
     else ks = {8, 10};          // longer seeds for reads that allow them: far fewer candidates to verify
-    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = n_refs; L.total = (u32)total;
     for (int k : ks) {
         if ((u64)k > total) continue;
         const u64 nb = 1ull << (2 * k);
@@ -624,6 +653,108 @@ int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_a
     CK(cudaGetLastError());
     ctx->annotated = false; ctx->tallied = false;
     return MIRGE_OK;
+}
+
+int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_ascii, const uint64_t *offsets)
+{
+    if (lib_id == MIRGE_LIB_GENOME) return fail(ctx, MIRGE_E_ARG, "mirge_load_library: slot 8 is the genome, use mirge_load_genome");
+    return load_library_impl(ctx, lib_id, n_refs, seq_ascii, offsets);
+}
+
+int mirge_load_genome(mirge_ctx *ctx, int n_refs, const char *seq_ascii, const uint64_t *offsets)
+{
+    return load_library_impl(ctx, MIRGE_LIB_GENOME, n_refs, seq_ascii, offsets);
+}
+
+// Shared tail of the genome passes: queries are packed in d_q* (n of them); counts come back to the host.
+template <int W>
+static int genome_pass_run(mirge_ctx *ctx, uint64_t n, const u64 *qs, const u64 *qnm, const u8 *qlen, const GenomeParams &P, uint32_t *counts_host)
+{
+    cudaStream_t st = ctx->stream;
+    const DevLib &l = ctx->libs[MIRGE_LIB_GENOME];
+    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = l.n_refs; L.total = l.total;
+    GenomeIndex X; X.off = l.gx_off; X.pos = l.gx_pos; X.kmax = l.gx_kmax;
+    u32 *d_counts = nullptr;
+    CK(cudaMalloc(&d_counts, (size_t)n * 4 * sizeof(u32)));
+    { ProfScope ps(ctx, KID_GENOME);
+      k2g_all_hits<W><<<grid_for(n * 32, K2G_THREADS, 148 * 16), K2G_THREADS, 0, st>>>(qs, qnm, qlen, n, L, X, P, d_counts); }
+    cudaError_t e = cudaMemcpyAsync(counts_host, d_counts, (size_t)n * 4 * sizeof(u32), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_counts);
+    if (e != cudaSuccess) { ctx->err = std::string("genome pass failed: ") + cudaGetErrorString(e); return MIRGE_E_CUDA; }
+    CK(cudaGetLastError());
+    return MIRGE_OK;
+}
+
+static int genome_params(mirge_ctx *ctx, int mode, int param, int seedlen, int trim3, int norc, GenomeParams &P)
+{
+    if ((mode != 0 && mode != 1) || param < 0 || param > 3 || seedlen < 1 || trim3 < 0) return fail(ctx, MIRGE_E_ARG, "mirge_genome_pass: bad argument");
+    if (!ctx->libs[MIRGE_LIB_GENOME].gx_off) return fail(ctx, MIRGE_E_STATE, "mirge_genome_pass: no genome loaded (mirge_load_genome)");
+    P.mode = mode; P.param = param; P.seedlen = seedlen; P.trim3 = trim3; P.norc = norc ? 1 : 0;
+    return MIRGE_OK;
+}
+
+int mirge_genome_pass(mirge_ctx *ctx, uint64_t n, const char *reads, int stride, const uint8_t *lens,
+                      int mode, int param, int seedlen, int trim3, int norc, uint32_t *counts)
+{
+    GenomeParams P;
+    int rc = genome_params(ctx, mode, param, seedlen, trim3, norc, P);
+    if (rc) return rc;
+    if (n == 0) return MIRGE_OK;
+    if (!reads || !lens || !counts || stride < 1) return fail(ctx, MIRGE_E_ARG, "mirge_genome_pass: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const int W = ctx->W, NW = W / 2;
+    std::vector<u64> hs((size_t)n * W, 0), hn((size_t)n * NW, 0);
+    for (uint64_t i = 0; i < n; i++) {
+        const int len = lens[i];
+        if (len > ctx->max_len || len > stride) return fail(ctx, MIRGE_E_TOOLONG, "mirge_genome_pass: a read is longer than max_read_len");
+        const char *r = reads + i * (uint64_t)stride;
+        for (int b = 0; b < len; b++) {
+            int c = base_code((unsigned char)r[b]);
+            if (c > 3) { hn[i * NW + (b >> 6)] |= 1ull << (b & 63); c = 0; }
+            hs[i * W + (b >> 5)] |= (u64)c << ((b & 31) * 2);
+        }
+    }
+    u64 *qs = nullptr, *qnm = nullptr; u8 *ql = nullptr;
+    CK(cudaMalloc(&qs, hs.size() * sizeof(u64)));
+    CK(cudaMalloc(&qnm, hn.size() * sizeof(u64)));
+    CK(cudaMalloc(&ql, (size_t)n));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(qs, hs.data(), hs.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(qnm, hn.data(), hn.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ql, lens, (size_t)n, cudaMemcpyHostToDevice, st));
+    rc = W == 2 ? genome_pass_run<2>(ctx, n, qs, qnm, ql, P, counts) : genome_pass_run<4>(ctx, n, qs, qnm, ql, P, counts);
+    cudaFree(qs); cudaFree(qnm); cudaFree(ql);
+    return rc;
+}
+
+int mirge_genome_pass_ids(mirge_ctx *ctx, uint64_t n, const uint32_t *ids, int mode, int param, int seedlen, int trim3, int norc,
+                          uint32_t *counts)
+{
+    GenomeParams P;
+    int rc = genome_params(ctx, mode, param, seedlen, trim3, norc, P);
+    if (rc) return rc;
+    if (n == 0) return MIRGE_OK;
+    if (!ids || !counts) return fail(ctx, MIRGE_E_ARG, "mirge_genome_pass_ids: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    u64 U = 0;
+    rc = mirge_get_stats(ctx, nullptr, nullptr, (uint64_t *)&U);
+    if (rc) return rc;
+    const int W = ctx->W, NW = W / 2;
+    u64 *qs = nullptr, *qnm = nullptr; u8 *ql = nullptr; u32 *d_ids = nullptr;
+    CK(cudaMalloc(&qs, (size_t)n * W * sizeof(u64)));
+    CK(cudaMalloc(&qnm, (size_t)n * NW * sizeof(u64)));
+    CK(cudaMalloc(&ql, (size_t)n));
+    CK(cudaMalloc(&d_ids, (size_t)n * sizeof(u32)));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_ids, ids, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, st));
+    const int g = grid_for(n, 256, 148 * 8);
+    ctx->n_launches++;
+    if (W == 2) k2g_gather_queries<2><<<g, 256, 0, st>>>(d_ids, n, ctx->d_useq, ctx->d_unmask, ctx->d_ulen, U, qs, qnm, ql);
+    else k2g_gather_queries<4><<<g, 256, 0, st>>>(d_ids, n, ctx->d_useq, ctx->d_unmask, ctx->d_ulen, U, qs, qnm, ql);
+    rc = W == 2 ? genome_pass_run<2>(ctx, n, qs, qnm, ql, P, counts) : genome_pass_run<4>(ctx, n, qs, qnm, ql, P, counts);
+    cudaFree(qs); cudaFree(qnm); cudaFree(ql); cudaFree(d_ids);
+    return rc;
 }
 
 struct RoundSpec { int lib, len_filter, mode, param, trim5, trim3, highest, polyT; };

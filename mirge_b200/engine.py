@@ -113,6 +113,38 @@ class Engine:
     def annotate(self):
         self._ck(lib.mirge_annotate(self.h))
 
+    # -- genome passes ------------------------------------------------------------
+    def load_genome(self, names, seqs):
+        """index.Libs/<sp>_genome (library slot 8)."""
+        off = np.zeros(len(seqs) + 1, np.uint64)
+        if len(seqs):
+            off[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+        cat = np.frombuffer(''.join(seqs).encode() or b'\0', dtype=np.uint8)
+        self._ck(lib.mirge_load_genome(self.h, len(seqs), _ptr(cat), _ptr(off)))
+        self.lib_names[8] = list(names)
+
+    def genome_pass(self, reads, mode=0, param=1, seedlen=28, trim3=0, norc=False):
+        """`bowtie genome -n/-v ... -a` for a list of sequences (str): counts[i][k] = alignments with k mismatches."""
+        n = len(reads)
+        counts = np.zeros((n, 4), np.uint32)
+        if n == 0:
+            return counts
+        lens = np.array([len(r) for r in reads], np.uint8)
+        stride = max(1, int(lens.max()))
+        buf = np.zeros((n, stride), np.uint8)
+        for i, r in enumerate(reads):
+            buf[i, :len(r)] = np.frombuffer(r.encode() if isinstance(r, str) else r, dtype=np.uint8)
+        self._ck(lib.mirge_genome_pass(self.h, n, _ptr(buf), stride, _ptr(lens), mode, param, seedlen, trim3, int(norc), _ptr(counts)))
+        return counts
+
+    def genome_pass_ids(self, ids, mode=0, param=1, seedlen=28, trim3=0, norc=False):
+        """Same for unique sequences of the device table (ids = row numbers of export_unique)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        counts = np.zeros((len(ids), 4), np.uint32)
+        if len(ids):
+            self._ck(lib.mirge_genome_pass_ids(self.h, len(ids), _ptr(ids), mode, param, seedlen, trim3, int(norc), _ptr(counts)))
+        return counts
+
     # -- stage 3 ----------------------------------------------------------------
     def tally(self):
         self._ck(lib.mirge_tally(self.h))
