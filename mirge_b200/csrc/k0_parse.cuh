@@ -35,11 +35,12 @@
 #pragma once
 #include "common.cuh"
 
-#define K0_THREADS 128
+#define K0_THREADS 256
 #define K0_TILE 16384
 #define K0_HALO 1024
 #define K0_UNITS ((K0_TILE + K0_HALO) / 16)
 #define K0_CAP 2048                 // line-start list entries per pass
+#define K0_MW (K0_TILE / K0_THREADS / 32)   // 32-bit newline-mask words of the bytes one thread ranks
 #define K0_NONE 0xFFFFu             // list entry: the line starts before the halo
 
 #define K0_ST_AGG (1ull << 62)      // tile status: newline count of this tile
@@ -162,6 +163,27 @@ __device__ __forceinline__ void k0_pack_record(F32 ld32, F8 ld8, u32 a0, u32 a1,
 __device__ __forceinline__ void k0_load_tile(const unsigned char *__restrict__ text, i64 halo_start, u64 reg_end, int vnl,
                                              unsigned char *buf, u16 *m16)
 {
+    constexpr int PER = K0_TILE / 16 / K0_THREADS;       // tile units per thread
+    if (halo_start >= 0 && (u64)halo_start + K0_HALO + K0_TILE <= reg_end) {
+        // interior tile: every load is issued before the first one is consumed (the copy is latency bound otherwise)
+        const uint4 *src = reinterpret_cast<const uint4 *>(text + halo_start);
+        uint4 v[PER + 1];
+#pragma unroll
+        for (int k = 0; k < PER; k++) v[k] = __ldg(src + K0_HALO / 16 + k * K0_THREADS + threadIdx.x);
+        v[PER] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x < K0_HALO / 16) v[PER] = __ldg(src + threadIdx.x);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int u = K0_HALO / 16 + k * K0_THREADS + threadIdx.x;
+            *reinterpret_cast<uint4 *>(buf + 16 * u) = v[k];
+            m16[u] = (u16)nl_mask_words(v[k].x, v[k].y, v[k].z, v[k].w);
+        }
+        if (threadIdx.x < K0_HALO / 16) {
+            *reinterpret_cast<uint4 *>(buf + 16 * threadIdx.x) = v[PER];
+            m16[threadIdx.x] = (u16)nl_mask_words(v[PER].x, v[PER].y, v[PER].z, v[PER].w);
+        }
+        return;
+    }
     for (int u = threadIdx.x; u < K0_UNITS; u += K0_THREADS) {
         const i64 g0 = halo_start + 16 * (i64)u;
         uint4 v = make_uint4(0, 0, 0, 0);
@@ -191,13 +213,13 @@ __device__ __forceinline__ void k0_fill_list(u32 pass_lo, u32 ex, const u32 *mw,
     const unsigned tid = threadIdx.x;
     u32 o = ex;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < K0_MW; k++) {
         u32 m = mw[k];
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
             const u32 li = o + 4 - pass_lo;
-            if (li < K0_CAP) lst[li] = (u16)(K0_HALO + 128 * tid + 32 * k + b + 1);
+            if (li < K0_CAP) lst[li] = (u16)(K0_HALO + (K0_TILE / K0_THREADS) * tid + 32 * k + b + 1);
             o++;
         }
     }
@@ -320,9 +342,12 @@ k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
         const i64 halo_start = (i64)tile_start - K0_HALO;
         k0_load_tile(text, halo_start, reg_end, vnl, buf, m16);
         __syncthreads();
-        const uint4 mm = *reinterpret_cast<const uint4 *>(m16 + K0_HALO / 16 + 8 * tid);   // this thread's 128 bytes
-        const u32 mw[4] = {mm.x, mm.y, mm.z, mm.w};
-        const u32 cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
+        u32 mw[K0_MW], cnt = 0;                                                             // this thread's K0_TILE / K0_THREADS bytes
+#pragma unroll
+        for (int k = 0; k < K0_MW; k++) {
+            mw[k] = *reinterpret_cast<const u32 *>(m16 + K0_HALO / 16 + 2 * K0_MW * tid + 2 * k);
+            cnt += __popc(mw[k]);
+        }
         u32 T;
         const u32 ex = block_excl_scan(cnt, sh_scan, &T);
         u32 o0 = K0_CLAIM_NONE;
@@ -427,9 +452,12 @@ k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
         k0_load_tile(text, halo_start, reg_end, vnl, buf, m16);
         __syncthreads();
         // rank the tile's newlines; chained scan over the tiles
-        const uint4 mm = *reinterpret_cast<const uint4 *>(m16 + K0_HALO / 16 + 8 * tid);   // this thread's 128 bytes
-        const u32 mw[4] = {mm.x, mm.y, mm.z, mm.w};
-        const u32 cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
+        u32 mw[K0_MW], cnt = 0;                                                             // this thread's K0_TILE / K0_THREADS bytes
+#pragma unroll
+        for (int k = 0; k < K0_MW; k++) {
+            mw[k] = *reinterpret_cast<const u32 *>(m16 + K0_HALO / 16 + 2 * K0_MW * tid + 2 * k);
+            cnt += __popc(mw[k]);
+        }
         u32 T;
         const u32 ex = block_excl_scan(cnt, sh_scan, &T);
         if (wid == 0) {
