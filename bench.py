@@ -377,7 +377,7 @@ def run_ours(args):
             'metric': METRIC, 'value': value, 'unit': 'reads/s', 'n_gpus': N, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_res / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u8/u64 (2-bit packed integer)', 'data': 'synthetic',
-            'config': {'workload': workload_name(args), 'reads_per_gpu': n_reads, 'unique_owned_rank0': U, 'kept_frac': float(k[sample]) / n_reads, 'k1_slow_path_frac': slow_frac, 'k1_class1_frac': cls[1] / float(n_reads), 'k1_class2_frac': cls[2] / float(n_reads),
+            'config': {'workload': workload_name(args), 'reads_per_gpu': n_reads, 'unique_owned_rank0': U, 'kept_frac': float(k[sample]) / n_reads, 'k1_slow_path_frac': slow_frac, 'k1_class1_frac': cls[1] / float(n_reads), 'k1_class2_frac': cls[2] / float(n_reads), 'k0_regions_reparsed_exactly': cls[3],
                        'l2_policy': 'inputs (%.2f GB FASTQ text per GPU) larger than the 126 MB L2' % (nbytes / 1e9),
                        'parallelism': 'reads sharded by sample across %d GPU(s); hash-partition all-to-all (X1) + device table all-reduce (X2), both inside the timed region' % N,
                        'cpus_bound_to_gpu_numa_node': n_cpus_bound,

@@ -191,10 +191,11 @@ int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const cha
  * NULL) receives the number of reads that went through the slow queue so far.
  * Results are identical in every mode. */
 int mirge_debug(mirge_ctx *ctx, int force_slow, uint64_t *slow_reads);
-/* Diagnostics of the trim kernel since the last reset: out3 = reads through the
- * all-column search, reads the prefilter sent to the full-candidate scan
- * (class 1), reads it sent to the general search (class 2).  Synchronises. */
-int mirge_trim_classes(mirge_ctx *ctx, uint64_t *out3);
+/* Diagnostics since the last reset: out4 = reads through the all-column search,
+ * reads the prefilter sent to the full-candidate scan (class 1), reads it sent
+ * to the general search (class 2), feed regions whose speculative parse was
+ * rejected and redone by the exact kernel (k0_parse.cuh).  Synchronises. */
+int mirge_trim_classes(mirge_ctx *ctx, uint64_t *out4);
 /* The tables behind the trim kernel's exact-match prefilter for ONE 3' adapter
  * (mirge_b200/csrc/k1_prefilter.cuh): returns 1 and fills m, icap, safe_p,
  * safe_len[49] (index = insert length I, bit l) and fullreach[32] (index = l)

@@ -99,18 +99,40 @@ def main(argv=None):
     from .engine import MirgeError
 
     samples = resolve_samples(args.sampleList)
-    outdir = os.path.join(os.path.abspath(args.output_dir), 'miRge.' + time.strftime('%Y-%m-%d_%H-%M-%S', time.localtime()))
+    # launched under torch.distributed.run: one process per GPU, the file chunks of every sample shard over the ranks
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    device = args.gpu
+    log = print
+    stamp = time.strftime('%Y-%m-%d_%H-%M-%S', time.localtime())
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        device = int(os.environ.get('LOCAL_RANK', rank))
+        torch.cuda.set_device(device)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', device))
+        box = [stamp]
+        dist.broadcast_object_list(box, src=0)          # one output directory name for the job
+        stamp = box[0]
+        if rank != 0:
+            log = lambda *a, **k: None                  # noqa: E731
+    outdir = os.path.join(os.path.abspath(args.output_dir), 'miRge.' + stamp)
     t0 = time.time()
     try:
         run = AnnotateRun(samples, args.libraryPath, args.species, db, adapter, args.spikeIn,
-                          max_unique=args.max_unique, device=args.gpu)
+                          max_unique=args.max_unique, device=device, log=log, rank=rank, world=world)
         if args.gff_output and not os.path.isfile(run.libdir.gff3):     # extractPreMiRName opens it unguarded (IOError upstream)
             raise LibraryError('%s does not exist: -gff needs the miRNA coordinate file.' % run.libdir.gff3)
-        os.mkdir(outdir)
+        if rank == 0:
+            os.mkdir(outdir)
         run.run()
         t1 = time.time()
-        print('Summarizing and tabulating results...')
+        log('Summarizing and tabulating results...')
         run.write_outputs(outdir, args.canoRatio, tcf=args.trimmed_collapsed_fa, isomir_diff=args.diff_isomirs, gff=args.gff_output)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+            if rank != 0:
+                return outdir
     except (LibraryError, GffError) as e:
         print(str(e))
         sys.exit(1)

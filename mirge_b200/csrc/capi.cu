@@ -78,8 +78,8 @@ struct mirge_ctx {
     u64 max_unique = 0;
     u64 *d_useq = nullptr, *d_unmask = nullptr; u8 *d_ulen = nullptr; u32 *d_counts = nullptr;
     signed char *d_round_of = nullptr, *d_mm_of = nullptr; int *d_ref_of = nullptr, *d_pos_of = nullptr;
-    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept, [2+S..5+S) K1 diagnostics (all-column search, class 1, class 2),
-    // [5+S..5+2S) processed
+    // counters: [0] n_unique, [1] err flags (low 32 bits), [2..2+S) kept, [2+S..6+S) diagnostics (K1: all-column search, class 1, class 2; K0: regions that took the exact path),
+    // [6+S..6+2S) processed
     u64 *d_ctr = nullptr;
     u64 *d_len_hist = nullptr;
     // mapping
@@ -279,7 +279,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_mm_of, max_unique));
     CK(cudaMalloc(&ctx->d_ref_of, max_unique * sizeof(int)));
     CK(cudaMalloc(&ctx->d_pos_of, max_unique * sizeof(int)));
-    CK(cudaMalloc(&ctx->d_ctr, (5 + 2 * (size_t)n_samples) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_ctr, (6 + 2 * (size_t)n_samples) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_len_hist, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64)));
     // to-do lists: every unique once, plus the partly used chunk of every appending warp
     CK(cudaMalloc(&ctx->d_todo[0], (max_unique + (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
@@ -291,7 +291,7 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_lib_totals, (size_t)n_samples * MIRGE_N_TOTALS * sizeof(i64)));
     CK(cudaMemsetAsync(ctx->d_slots, 0, cap * esz, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counts, 0, max_unique * (size_t)n_samples * sizeof(u32), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_ctr, 0, (5 + 2 * (size_t)n_samples) * sizeof(u64), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (6 + 2 * (size_t)n_samples) * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -467,7 +467,7 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
     const int k0_grid = wave_grid(k0_parse_pack<W>, K0_THREADS, 1ull << 40), k0s_grid = wave_grid(k0_parse_spec<W>, K0_THREADS, 1ull << 40);
     const bool exact_only = (ctx->force_slow & 0x2000) != 0;          // test hook: skip the speculation
     u32 *err_flags = (u32 *)(ctx->d_ctr + 1);
-    u64 *processed = ctx->d_ctr + 5 + ctx->S + sample;
+    u64 *processed = ctx->d_ctr + 6 + ctx->S + sample;
     for (int r = 0; r < nreg; r++) {
         const u64 a = (u64)r * region, len = (a + region <= nbytes) ? region : nbytes - a;
         if (host_src) CK(cudaStreamWaitEvent(st, ctx->copy_events[r], 0));
@@ -480,7 +480,7 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
           if (!exact_only) {
               k0_parse_spec<W><<<grid_for((u64)ntiles * K0_THREADS, K0_THREADS, k0s_grid), K0_THREADS, 0, st>>>(
                   d_text, a, a + len, vnl, ntiles, ctx->d_k0info, ctx->d_k0state, kp, ctx->rec_cap, ctx->d_bases, ctx->d_nmask, ctx->d_meta);
-              k0_verify<<<1, 1024, 0, st>>>(ctx->d_k0info, ntiles, ctx->d_k0state, r & 1, last ? 1 : 0, err_flags, processed);
+              k0_verify<<<1, 1024, 0, st>>>(ctx->d_k0info, ntiles, ctx->d_k0state, r & 1, last ? 1 : 0, err_flags, processed, ctx->d_ctr + 5 + ctx->S);
           }
           k0_parse_pack<W><<<grid_for((u64)ntiles * K0_THREADS, K0_THREADS, k0_grid), K0_THREADS, 0, st>>>(
               d_text, a, a + len, vnl, last ? 1 : 0, ntiles, ctx->d_k0ctl, ctx->d_k0state, r & 1, kp, ctx->rec_cap,
@@ -539,11 +539,11 @@ int mirge_get_stats(mirge_ctx *ctx, uint64_t *processed, uint64_t *kept, uint64_
 {
     int rc = mirge_sync(ctx);
     if (rc) return rc;
-    std::vector<u64> h(5 + 2 * ctx->S);
+    std::vector<u64> h(6 + 2 * ctx->S);
     CK(cudaMemcpy(h.data(), ctx->d_ctr, h.size() * sizeof(u64), cudaMemcpyDeviceToHost));
     if (n_unique) *n_unique = h[0] < ctx->max_unique ? h[0] : ctx->max_unique;
     for (int s = 0; s < ctx->S; s++) {
-        if (processed) processed[s] = h[5 + ctx->S + s];
+        if (processed) processed[s] = h[6 + ctx->S + s];
         if (kept) kept[s] = h[2 + s];
     }
     return MIRGE_OK;
@@ -995,7 +995,7 @@ int mirge_reset(mirge_ctx *ctx)
     int rc = mirge_reset_unique(ctx);
     if (rc) return rc;
     cudaStream_t st = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_ctr, 0, (5 + 2 * (size_t)ctx->S) * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, (6 + 2 * (size_t)ctx->S) * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * ctx->S * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), st));
     return MIRGE_OK;
@@ -1014,11 +1014,11 @@ int mirge_debug(mirge_ctx *ctx, int force_slow, uint64_t *slow_reads)
     return MIRGE_OK;
 }
 
-int mirge_trim_classes(mirge_ctx *ctx, uint64_t *out3)
+int mirge_trim_classes(mirge_ctx *ctx, uint64_t *out4)
 {
     int rc = mirge_sync(ctx);
     if (rc) return rc;
-    CK(cudaMemcpy(out3, ctx->d_ctr + 2 + ctx->S, 3 * sizeof(u64), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out4, ctx->d_ctr + 2 + ctx->S, 4 * sizeof(u64), cudaMemcpyDeviceToHost));
     return MIRGE_OK;
 }
 
@@ -1058,7 +1058,7 @@ static void table_pieces(mirge_ctx *ctx, void **ptr, size_t *words)
     ptr[2] = ctx->d_lib_totals; words[2] = S * MIRGE_N_TOTALS;
     ptr[3] = ctx->d_len_hist; words[3] = (size_t)(ctx->max_len + 1) * S;
     ptr[4] = ctx->d_ctr + 2; words[4] = S;                  // kept
-    ptr[5] = ctx->d_ctr + 5 + S; words[5] = S;              // processed
+    ptr[5] = ctx->d_ctr + 6 + S; words[5] = S;              // processed
 }
 
 uint64_t mirge_tables_words(const mirge_ctx *ctx)

@@ -31,7 +31,7 @@
 //                   look-back, seeded with the line count carried over from the previous launch.  It is
 //                   launched after every k0_verify and returns at once unless asked for.
 // Records longer than the halo (kilobyte headers) take a byte-wise path through global memory; tiles
-// with more newlines than the list holds (reads of a few bases) are processed in several passes.
+// with more than 256 records (reads of a few bases) are processed in several passes.
 #pragma once
 #include "common.cuh"
 
@@ -39,7 +39,8 @@
 #define K0_TILE 16384
 #define K0_HALO 1024
 #define K0_UNITS ((K0_TILE + K0_HALO) / 16)
-#define K0_CAP 2048                 // line-start list entries per pass
+#define K0_RPP 256                  // records per pass: one per thread in the per-record phases
+#define K0_CAP (4 * K0_RPP + 4)      // line-start list entries per pass
 #define K0_MW (K0_TILE / K0_THREADS / 32)   // 32-bit newline-mask words of the bytes one thread ranks
 #define K0_NONE 0xFFFFu             // list entry: the line starts before the halo
 
@@ -65,17 +66,40 @@ struct K0State {
 #define K0_CLAIM_NONE 4u        // none of the tile's (fewer than four) newlines ends a record
 #define K0_CLAIM_UNDECIDED 5u   // a candidate could not be tested inside the halo
 
+// 0x80 in every byte of x that is zero (exact for every byte, no borrow between bytes)
+__device__ __forceinline__ u32 zero_bytes80(u32 x)
+{
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+
 __device__ __forceinline__ u32 nl_mask_words(u32 x, u32 y, u32 z, u32 w)
 {
+    const u32 f0 = zero_bytes80(x ^ 0x0A0A0A0Au), f1 = zero_bytes80(y ^ 0x0A0A0A0Au);
+    const u32 f2 = zero_bytes80(z ^ 0x0A0A0A0Au), f3 = zero_bytes80(w ^ 0x0A0A0A0Au);
+    if (!(f0 | f1 | f2 | f3)) return 0;                  // most 16-byte units hold no newline
     u32 m = 0;
-    const u32 v[4] = {x, y, z, w};
+    const u32 f[4] = {f0, f1, f2, f3};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const u32 eq = __vcmpeq4(v[k], 0x0A0A0A0Au);                 // 0xFF per matching byte
-        const u32 bits = ((eq & 0x01010101u) * 0x01020408u) >> 24;    // gather 4 flag bits
-        m |= (bits & 0xFu) << (4 * k);
-    }
+    for (int k = 0; k < 4; k++) m |= ((((f[k] >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * k);   // gather the 4 flag bits
     return m;
+}
+
+// Four ASCII bytes -> 2-bit codes (A=0 C=1 G=2 T/U=3, either case; 8 bits) and non-ACGTU flags (4 bits).
+// The code comes from bits 1-2 of the byte; a byte is a base iff it equals the letter its code stands for: the
+// expected letters are fetched with one PRMT (the codes as selector nibbles) and compared with bit 0 forced to one
+// (T and U differ there only), and bit 0 must be set unless the code is 3 ('@', 'B', 'F' are not A, C, G).
+__device__ __forceinline__ void k0_code4(u32 v, u32 &packed8, u32 &nbits4)
+{
+    const u32 c = ((v >> 1) ^ (v >> 2)) & 0x03030303u;
+    const u32 t = c | (c >> 4);
+    const u32 sel = (t & 0x00FFu) | ((t >> 8) & 0xFF00u);
+    const u32 expect = __byte_perm(0x55474341u, 0u, sel);
+    const u32 up = v & 0xDFDFDFDFu;
+    const u32 z = zero_bytes80((up | 0x01010101u) ^ expect);
+    const u32 ok80 = z & (((up | (c & (c >> 1))) & 0x01010101u) << 7);
+    const u32 okm = (ok80 >> 7) | (ok80 >> 6);           // 0x03 per valid byte
+    packed8 = ((c & okm) * 0x01041040u) >> 24;
+    nbits4 = ((((~ok80) & 0x80808080u) >> 7) * 0x01020408u) >> 24 & 0xFu;
 }
 
 __device__ __forceinline__ u64 k0_ld_status(const u64 *p)
@@ -120,12 +144,8 @@ __device__ __forceinline__ void k0_pack_record(F32 ld32, F8 ld8, u32 a0, u32 a1,
                 const u32 wnext = ld32(t0 + 4u * (u32)(gi + 1));
                 const u32 v = __funnelshift_r(wprev, wnext, sh8);       // bytes a1+4gi .. a1+4gi+3
                 wprev = wnext;
-                const u32 up = v & 0xDFDFDFDFu;
-                const u32 ok = __vcmpeq4(up, 0x41414141u) | __vcmpeq4(up, 0x43434343u) | __vcmpeq4(up, 0x47474747u) |
-                               __vcmpeq4(up, 0x54545454u) | __vcmpeq4(up, 0x55555555u);        // A C G T U
-                const u32 code = (((v >> 1) ^ (v >> 2)) & 0x03030303u) & ok;   // A=0 C=1 G=2 T/U=3, others 0
-                u32 packed = (code * 0x01041040u) >> 24;                        // 4 x 2 bits
-                u32 nbits = (((~ok) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu;
+                u32 packed, nbits;
+                k0_code4(v, packed, nbits);
                 const int left = sl - gi * 4;
                 if (left < 4) { packed &= (1u << (2 * left)) - 1u; nbits &= (1u << left) - 1u; }
                 acc |= (u64)packed << ((gi & 7) * 8);
@@ -241,33 +261,75 @@ __device__ __forceinline__ void k0_fill_list(u32 pass_lo, u32 ex, const u32 *mw,
     }
 }
 
-// 4. the records whose terminating newline has ordinal o in [pass_lo, pass_lo + K0_CAP - 4) and
-// o = o0 (mod 4): record with ordinal o goes to slot slot0 + (o - o0) / 4.
+// Per-pass staging area in shared memory: the records of one pass in their final layout.
+template <int W>
+struct K0Stage {
+    u64 bases[K0_RPP * W];
+    u64 nmask[K0_RPP * (W / 2)];
+    u32 meta[K0_RPP];
+    u16 a1[K0_RPP];         // shared offset of the record's sequence line
+    u8 sl[K0_RPP];          // bases to pack (0: none); K0_SL_DONE: phase A filled the stage itself (global path)
+};
+#define K0_SL_DONE 0xFFu
+
+// 4. the records whose terminating newline has ordinal o in [pass_lo, pass_lo + K0_CAP - 4) and o = o0 (mod 4);
+// the record with ordinal o goes to slot slot0 + (o - o0) / 4.  Three phases:
+//   A  one thread per record: format checks, lengths, quality_trim_index -> meta, (a1, sl) for phase B
+//   B  one thread per 8 bases: two aligned-word groups -> 16 bits of bases + 8 N flags, stored in place in the stage
+//      (short critical path, nearly all lanes busy -- a thread per record leaves half of them idle for 13 steps)
+//   C  the stage goes out as three flat, coalesced copies
 template <int W>
 __device__ __forceinline__ void k0_pack_pass(const unsigned char *__restrict__ text, u64 reg_end, i64 delta, const unsigned char *buf,
                                              const u16 *lst, u32 pass_lo, u32 o0, u32 T, u64 slot0, u64 rec_cap, const K0Params &prm,
-                                             u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta, u32 *err_word)
+                                             K0Stage<W> &st, u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta,
+                                             u32 *err_word)
 {
     constexpr int NW = W / 2;
     const unsigned tid = threadIdx.x;
     const u32 lo = pass_lo > o0 ? pass_lo + ((o0 + 4 - (pass_lo & 3)) & 3) : o0;
     u32 hi = pass_lo + K0_CAP - 4;
     if (hi > T) hi = T;
-    for (u32 o = lo + 4 * tid; o < hi; o += 4 * K0_THREADS) {
-        const u64 slot = slot0 + ((o - o0) >> 2);
-        const u32 li = o + 4 - pass_lo;
+    const u32 nrec = hi > lo ? (hi - lo + 3) >> 2 : 0u;        // <= K0_RPP
+    if (nrec == 0) return;                                     // block-uniform
+    const u64 slotp = slot0 + ((lo - o0) >> 2);
+    // ---- A
+    if (tid < nrec) {
+        const u32 li = lo + 4 * tid + 4 - pass_lo;
         u32 l[5];
 #pragma unroll
         for (int k = 0; k < 5; k++) l[k] = lst[li - 4 + k];
-        u64 s[W], nm[NW];
-        u32 mt, bad;
+        u32 bad = 0, mt = 0;
         if (l[0] != K0_NONE) {
-            const unsigned char *b0 = buf;
-            auto ld32 = [b0](u32 off) { return *reinterpret_cast<const u32 *>(b0 + off); };
-            auto ld8 = [b0](u32 off) { return (u32)b0[off]; };
-            k0_pack_record<W>(ld32, ld8, l[0], l[1], l[2], l[3], l[4], prm, s, nm, mt, bad);
+            const u32 a0 = l[0], a1 = l[1], a2 = l[2], a3 = l[3], a4 = l[4];
+            if (buf[a0] != '@' || buf[a2] != '+') bad |= ERRF_FORMAT;       // cutadapt FormatError
+            int sl = (int)(a2 - 1 - a1), ql = (int)(a4 - 1 - a3);
+            while (sl > 0 && buf[a1 + sl - 1] == '\r') sl--;
+            while (ql > 0 && buf[a3 + ql - 1] == '\r') ql--;
+            if (sl != ql) bad |= ERRF_FORMAT;
+            if (sl > prm.max_len) { bad |= ERRF_TOOLONG; sl = 0; }
+            if (bad) sl = 0;
+            // quality_trim_index(qualities, cutoff_front=0, cutoff_back, base)
+            int start = 0, stop = sl;
+            {
+                int acc = 0, mx = 0;
+                for (int i = 0; i < sl; i++) {
+                    acc += 0 - ((int)buf[a3 + i] - prm.phred_base);
+                    if (acc < 0) break;
+                    if (acc > mx) { mx = acc; start = i + 1; }
+                }
+                acc = 0; mx = 0;
+                for (int i = sl - 1; i >= 0; i--) {
+                    acc += prm.qual_cutoff - ((int)buf[a3 + i] - prm.phred_base);
+                    if (acc < 0) break;
+                    if (acc > mx) { mx = acc; stop = i; }
+                }
+                if (start >= stop) { start = 0; stop = 0; }
+            }
+            mt = (u32)sl | ((u32)start << 8) | ((u32)stop << 16);
+            st.a1[tid] = (u16)a1;
+            st.sl[tid] = (u8)sl;
         } else {
-            // a line of this record starts before the halo: find the missing starts in global memory
+            // a line of this record starts before the halo: find the missing starts in global memory, pack byte-wise
             u64 g[5];
             g[4] = (u64)((i64)l[4] + delta);
             for (int k = 3; k >= 0; k--) {
@@ -281,28 +343,62 @@ __device__ __forceinline__ void k0_pack_pass(const unsigned char *__restrict__ t
             const u64 lim = reg_end;
             auto ld8 = [tb, gb, lim](u32 off) { return gb + off < lim ? (u32)tb[off] : 0u; };
             auto ld32 = [ld8](u32 off) { return ld8(off) | (ld8(off + 1) << 8) | (ld8(off + 2) << 16) | (ld8(off + 3) << 24); };
-            if (g[4] - gb >= 0xFFFFFF00ull) {
-                bad = ERRF_FORMAT; mt = 0;
+            u64 sq[W], nq[NW];
 #pragma unroll
-                for (int w = 0; w < W; w++) s[w] = 0;
+            for (int w = 0; w < W; w++) sq[w] = 0;
 #pragma unroll
-                for (int w = 0; w < NW; w++) nm[w] = 0;
-            } else {
-                k0_pack_record<W>(ld32, ld8, (u32)(g[0] - gb), (u32)(g[1] - gb), (u32)(g[2] - gb), (u32)(g[3] - gb), (u32)(g[4] - gb),
-                                  prm, s, nm, mt, bad);
-            }
+            for (int w = 0; w < NW; w++) nq[w] = 0;
+            if (g[4] - gb >= 0xFFFFFF00ull) bad = ERRF_FORMAT;
+            else k0_pack_record<W>(ld32, ld8, (u32)(g[0] - gb), (u32)(g[1] - gb), (u32)(g[2] - gb), (u32)(g[3] - gb), (u32)(g[4] - gb),
+                                   prm, sq, nq, mt, bad);
+#pragma unroll
+            for (int w = 0; w < W; w++) st.bases[tid * W + w] = sq[w];
+#pragma unroll
+            for (int w = 0; w < NW; w++) st.nmask[tid * NW + w] = nq[w];
+            st.a1[tid] = 0;
+            st.sl[tid] = (u8)K0_SL_DONE;
         }
+        st.meta[tid] = mt;
         if (bad) atomicOr(err_word, bad);
-        if (slot < rec_cap) {
-            if (W == 2) *reinterpret_cast<ulonglong2 *>(bases + slot * 2) = make_ulonglong2(s[0], s[1]);
-            else {
-#pragma unroll
-                for (int w = 0; w < W; w++) bases[slot * W + w] = s[w];
+    }
+    __syncthreads();
+    // ---- B
+    {
+        u16 *sb = reinterpret_cast<u16 *>(st.bases);
+        u8 *sn = reinterpret_cast<u8 *>(st.nmask);
+        for (u32 it = tid; it < nrec * (4 * W); it += K0_THREADS) {
+            const u32 rec = it / (4 * W), pr = it % (4 * W);
+            const u32 sl = st.sl[rec];
+            if (sl == K0_SL_DONE) continue;
+            u32 p16 = 0, n8 = 0;
+            const int left = (int)sl - 8 * (int)pr;
+            if (left > 0) {
+                const u32 a = (u32)st.a1[rec] + 8 * pr;
+                const u32 t0 = a & ~3u, sh8 = (a & 3u) * 8u;
+                const u32 w0 = *reinterpret_cast<const u32 *>(buf + t0), w1 = *reinterpret_cast<const u32 *>(buf + t0 + 4);
+                const u32 w2 = *reinterpret_cast<const u32 *>(buf + t0 + 8);
+                u32 pa, na, pb, nb;
+                k0_code4(__funnelshift_r(w0, w1, sh8), pa, na);
+                k0_code4(__funnelshift_r(w1, w2, sh8), pb, nb);
+                p16 = pa | (pb << 8);
+                n8 = na | (nb << 4);
+                if (left < 8) { p16 &= (1u << (2 * left)) - 1u; n8 &= (1u << left) - 1u; }
             }
-#pragma unroll
-            for (int w = 0; w < NW; w++) nmask[slot * NW + w] = nm[w];
-            meta[slot] = mt;
-        } else atomicOr(err_word, ERRF_FORMAT);
+            sb[it] = (u16)p16;
+            sn[it] = (u8)n8;
+        }
+    }
+    __syncthreads();
+    // ---- C
+    {
+        u32 n_out = nrec;
+        if (slotp + nrec > rec_cap) {
+            if (tid == 0) atomicOr(err_word, ERRF_FORMAT);
+            n_out = slotp < rec_cap ? (u32)(rec_cap - slotp) : 0u;
+        }
+        for (u32 i = tid; i < n_out * W; i += K0_THREADS) bases[slotp * W + i] = st.bases[i];
+        for (u32 i = tid; i < n_out * NW; i += K0_THREADS) nmask[slotp * NW + i] = st.nmask[i];
+        for (u32 i = tid; i < n_out; i += K0_THREADS) meta[slotp + i] = st.meta[i];
     }
 }
 
@@ -336,6 +432,7 @@ k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
     __shared__ u32 sh_scan[33];
     __shared__ u32 sh_claim;
     __shared__ u64 sh_slot0;
+    __shared__ K0Stage<W> stage;
     const unsigned tid = threadIdx.x;
     for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const u64 tile_start = reg_start + (u64)tile * K0_TILE;
@@ -372,7 +469,7 @@ k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
                 o0 = sh_claim; slot0 = sh_slot0;
             }
             if (o0 < 4)
-                k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, slot0, rec_cap, prm, bases, nmask, meta, &state->err_spec);
+                k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, slot0, rec_cap, prm, stage, bases, nmask, meta, &state->err_spec);
             __syncthreads();
         }
     }
@@ -382,7 +479,7 @@ k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
 // speculative launch.  One CTA.
 __global__ void __launch_bounds__(1024)
 k0_verify(const u32 *__restrict__ info, u32 ntiles, K0State *__restrict__ state, int par, int last_region,
-          u32 *__restrict__ err_flags, u64 *__restrict__ processed)
+          u32 *__restrict__ err_flags, u64 *__restrict__ processed, u64 *__restrict__ n_exact)
 {
     __shared__ u32 sh_scan[33];
     const u64 lines_in = state->lines[par];
@@ -408,7 +505,7 @@ k0_verify(const u32 *__restrict__ info, u32 ntiles, K0State *__restrict__ state,
     }
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
-        if (bad) state->need_exact = 1u;
+        if (bad) { state->need_exact = 1u; atomicAdd(n_exact, 1ull); }
         else {
             const u64 lines_out = lines_in + carry;
             state->need_exact = 0u;
@@ -437,6 +534,7 @@ k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
     __shared__ u32 sh_scan[33];
     __shared__ u32 sh_tile;
     __shared__ u64 sh_excl;
+    __shared__ K0Stage<W> stage;
     if (!always && !state->need_exact) return;
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const u64 lines_in = state->lines[par];
@@ -492,7 +590,7 @@ k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
             __syncthreads();
             const u64 G = sh_excl;
             const u32 o0 = (u32)((3ull - (G & 3ull)) & 3ull);        // first record-terminating newline of the tile
-            k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, ((G + o0) >> 2) - rec0, rec_cap, prm, bases, nmask, meta, err_flags);
+            k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, ((G + o0) >> 2) - rec0, rec_cap, prm, stage, bases, nmask, meta, err_flags);
             __syncthreads();
         }
         if (tile == ntiles - 1 && tid == 0) {                // hand the line count on to the next launch

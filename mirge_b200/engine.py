@@ -227,8 +227,9 @@ class Engine:
         self._ck(lib.mirge_debug(self.h, int(mode), None))
 
     def trim_classes(self):
-        """(reads through the all-column search, prefilter class-1 reads, prefilter class-2 reads)."""
-        n = np.zeros(3, np.uint64)
+        """(reads through the all-column search, prefilter class-1 reads, prefilter class-2 reads, feed regions
+        re-parsed by the exact K0 kernel)."""
+        n = np.zeros(4, np.uint64)
         self._ck(lib.mirge_trim_classes(self.h, _ptr(n)))
         return tuple(int(x) for x in n)
 

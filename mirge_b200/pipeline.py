@@ -44,6 +44,85 @@ def iter_fastq_chunks(path, chunk_bytes=CHUNK_BYTES):
         yield carry     # last record without a trailing newline
 
 
+def find_record_start(f, offset, size, window=1 << 18):
+    """First record boundary at or after byte `offset` of an uncompressed FASTQ file: the start of a line that begins
+    with '@', whose line after next begins with '+', whose sequence and quality lines are equally long -- and, when
+    visible, whose successor looks the same (a quality line may begin with '@'; a sequence line never begins with '+')."""
+    if offset <= 0:
+        return 0
+    if offset >= size:
+        return size
+    f.seek(offset - 1)
+    buf = f.read(window + 1)
+    nl = buf.find(b'\n')                                  # buf[0] is the byte before `offset`
+    if nl < 0:
+        return size
+    starts = [nl + 1]
+    while len(starts) < 16:
+        nl = buf.find(b'\n', starts[-1])
+        if nl < 0:
+            break
+        starts.append(nl + 1)
+
+    def line(i):
+        return buf[starts[i]:starts[i + 1] - 1].rstrip(b'\r')
+
+    def looks_like_record(i):
+        if i + 4 >= len(starts):
+            return None
+        return buf[starts[i]:starts[i] + 1] == b'@' and buf[starts[i + 2]:starts[i + 2] + 1] == b'+' and len(line(i + 1)) == len(line(i + 3))
+
+    for i in range(4):
+        a = looks_like_record(i)
+        if a is None:
+            break
+        b = looks_like_record(i + 4)
+        if a and b is not False:
+            return offset - 1 + starts[i]
+    raise MirgeError(-3, 'cannot find a FASTQ record boundary near byte %d (records longer than %d bytes?)' % (offset, window // 8))
+
+
+def iter_fastq_chunks_shard(path, rank, world, chunk_bytes=CHUNK_BYTES):
+    """Record-aligned chunks of this rank's share of one sample: an uncompressed file is cut into `world` byte ranges
+    whose ends are moved to record boundaries; a .gz stream cannot be entered in the middle, so every rank inflates it
+    and keeps every world-th chunk."""
+    if world <= 1:
+        yield from iter_fastq_chunks(path, chunk_bytes)
+        return
+    if path.endswith('.gz'):
+        per = max(1 << 20, chunk_bytes // world)
+        for k, chunk in enumerate(iter_fastq_chunks(path, per)):
+            if k % world == rank:
+                yield chunk
+        return
+    size = os.path.getsize(path)
+    with open(path, 'rb') as f:
+        lo = find_record_start(f, size * rank // world, size)
+        hi = find_record_start(f, size * (rank + 1) // world, size)
+        f.seek(lo)
+        carry = b''
+        left = hi - lo
+        while left > 0:
+            data = f.read(min(chunk_bytes, left))
+            if not data:
+                break
+            left -= len(data)
+            buf = carry + data
+            if left == 0:
+                yield buf
+                carry = b''
+                break
+            n_nl = buf.count(b'\n')
+            cut = buf.rfind(b'\n') + 1
+            for _ in range(n_nl % 4):
+                cut = buf.rfind(b'\n', 0, cut - 1) + 1
+            if cut > 0:
+                yield buf[:cut]
+            carry = buf[cut:]
+        if carry:
+            yield carry
+
+
 def peek_max_read_len(paths, n_records=2000):
     mx = 0
     for p in paths:
@@ -61,7 +140,9 @@ class AnnotateRun:
     """State of one `miRge2.0 annotate` run: the Engine plus the host-side names."""
 
     def __init__(self, sample_paths, library_path, species, db='miRBase', adapter='none', spike_in=False,
-                 max_unique=None, max_read_len=None, device=0, log=print):
+                 max_unique=None, max_read_len=None, device=0, log=print, rank=0, world=1):
+        self.rank, self.world = int(rank), int(world)
+        self._stream = None
         self.sample_paths = list(sample_paths)
         self.sample_names = []
         for p in self.sample_paths:     # __main__.py:339-345
@@ -89,6 +170,11 @@ class AnnotateRun:
         if self.engine is not None:
             self.engine.close()
         e = Engine(len(self.sample_paths), self.spike_in, self.max_unique, max(self.max_read_len, 1), self.device)
+        if self.world > 1:          # the exchange runs torch.distributed collectives: everything on one torch stream
+            import torch
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=torch.device('cuda', self.device))
+            e.set_stream(self._stream.cuda_stream)
         e.set_adapter(self.adapter)
         for t in self.libdir.types:
             names, seqs = self.libdir.load(t)
@@ -100,7 +186,11 @@ class AnnotateRun:
         """trim_file + quantReads for one sample (trim_file.py:89, quantReads.py:3):
         returns (phred, processed, kept) like trim_file."""
         phred = None
-        for chunk in iter_fastq_chunks(infile):
+        if self.world > 1:                                # decided by read #0 of the FILE on every rank, trim_file.py:104-109
+            opener = gzip.open if infile.endswith('.gz') else open
+            with opener(infile, 'rb') as f:
+                phred = Engine.detect_phred(f.read(1 << 16))
+        for chunk in iter_fastq_chunks_shard(infile, self.rank, self.world):
             if phred is None:
                 phred = Engine.detect_phred(chunk)        # decided by read #0, trim_file.py:104-109
             self.engine.feed_fastq(sample_index, chunk, phred)
@@ -108,42 +198,88 @@ class AnnotateRun:
         p, k, _ = self.engine.stats()
         return (phred or 33), int(p[sample_index]), int(k[sample_index])
 
+    def _agree(self, code):
+        """Distributed runs: every rank learns the most severe error code of the phase (0 = fine)."""
+        if self.world <= 1:
+            return code
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([code], dtype=torch.int64, device=torch.device('cuda', self.device))
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
+
     def run(self):
-        """Trim+collapse every sample, annotate, tally.  Grows the table and restarts when it fills up."""
+        """Trim+collapse every sample (this rank's file chunks), exchange (X1), annotate, tally, reduce (X2).  Grows the
+        table and restarts when it fills up -- on every rank alike."""
+        import contextlib
         while True:
-            try:
-                self._new_engine()
-                t0 = time.time()
-                for i, path in enumerate(self.sample_paths):
-                    self.log('Performing quantitation analysis of %s...' % self.sample_names[i])
-                    t1 = time.time()
-                    self.trim_file(path, i)
-                    self.log('It takes: %.2fs' % (time.time() - t1))
-                self.log('\nPerforming annotation for all of the collasped sequences...')
-                t2 = time.time()
-                self.engine.annotate()
-                self.engine.sync()
-                self.log('All annotation cycles completed (%.2f sec).\n' % (time.time() - t2))
-                self.engine.tally()
-                self.engine.sync()
-                self.timers = {'quant': t2 - t0, 'annotate': time.time() - t2}
-                return self
-            except MirgeError as e:
-                if e.code == -4 and self.max_read_len <= 64:
-                    # a read beyond the first 2000 records is longer than 64 nt (peek_max_read_len only samples):
-                    # rerun with the 128-nt record layout; longer reads remain the one hard limit
-                    self.max_read_len = 128
-                    self.log('a read is longer than 64 nt; retrying with max_read_len=128')
-                    continue
-                if e.code != -5 or self.max_unique >= (1 << 31):
-                    raise
-                self.max_unique *= 2
-                self.log('unique-sequence table full; retrying with max_unique=%d' % self.max_unique)
+            code, err = 0, None
+            self._new_engine()
+            scope = contextlib.nullcontext()
+            if self.world > 1:
+                import torch
+                scope = torch.cuda.stream(self._stream)
+            with scope:
+                try:
+                    t0 = time.time()
+                    for i, path in enumerate(self.sample_paths):
+                        self.log('Performing quantitation analysis of %s...' % self.sample_names[i])
+                        t1 = time.time()
+                        self.trim_file(path, i)
+                        self.log('It takes: %.2fs' % (time.time() - t1))
+                except MirgeError as e:
+                    code, err = e.code, e
+                code = self._agree(code)
+                if code == 0:
+                    try:
+                        if self.world > 1:
+                            from . import dist as mdist
+                            mdist.hash_partition(self.engine)
+                        self.log('\nPerforming annotation for all of the collasped sequences...')
+                        t2 = time.time()
+                        self.engine.annotate()
+                        self.engine.sync()
+                        self.log('All annotation cycles completed (%.2f sec).\n' % (time.time() - t2))
+                        self.engine.tally()
+                        if self.world > 1:
+                            mdist.reduce_engine_tables(self.engine)
+                        self.engine.sync()
+                        self.timers = {'quant': t2 - t0, 'annotate': time.time() - t2}
+                    except MirgeError as e:
+                        code, err = e.code, e
+                    code = self._agree(code)
+                    if code == 0:
+                        return self
+            if code == -4 and self.max_read_len <= 64:
+                # a read beyond the first 2000 records is longer than 64 nt (peek_max_read_len only samples):
+                # rerun with the 128-nt record layout; longer reads remain the one hard limit
+                self.max_read_len = 128
+                self.log('a read is longer than 64 nt; retrying with max_read_len=128')
+                continue
+            if code != -5 or self.max_unique >= (1 << 31):
+                raise err if err is not None else MirgeError(code, 'another rank failed')
+            self.max_unique *= 2
+            self.log('unique-sequence table full; retrying with max_unique=%d' % self.max_unique)
+
+    def gather_unique(self):
+        """export_unique() of the whole job on rank 0 (None elsewhere): every sequence is owned by exactly one rank."""
+        uniq = self.engine.export_unique()
+        if self.world <= 1:
+            return uniq
+        import torch.distributed as dist
+        parts = [None] * self.world if self.rank == 0 else None
+        dist.gather_object(uniq, parts, dst=0)
+        if self.rank != 0:
+            return None
+        return {k: np.concatenate([p[k] for p in parts]) for k in uniq}
 
     # -- outputs ------------------------------------------------------------------
     def write_outputs(self, outdir, cano_ratio='0.1', tcf=False, isomir_diff=False, gff=False):
         """summarize -> miRNAmerge -> filter -> generateReport / writeDataToCSV (__main__.py:381-389)."""
         e = self.engine
+        uniq = self.gather_unique()
+        if self.rank != 0:
+            return None
         p, k, _ = e.stats()
         t = e.export_tables()
         names = e.lib_names[0]
@@ -158,7 +294,6 @@ class AnnotateRun:
         tables.filter_mirnas(mirDic, self.sample_names, logDic, cano_ratio)
         with open(os.path.join(outdir, 'annotation.report.csv'), 'w') as f:
             f.write(tables.annotation_report(self.sample_names, logDic, self.spike_in))
-        uniq = e.export_unique()
         tables.write_mapped_unmapped(outdir, uniq, e.lib_names, self.annot_name_list, self.sample_names, self.spike_in)
         if isomir_diff:
             tables.write_isomirs(outdir, uniq, e.lib_names, self.sample_names, logDic)
