@@ -246,8 +246,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world_size > 1:
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep stdout to the one JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')           # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     N, S = world_size, world_size            # one sample per rank (weak scaling)
     world = build_world(args)

@@ -4,7 +4,7 @@ src/mirge/__main__.py:73-392), served by the CUDA pipeline.
 Same flags, same library-directory layout, same output directory
 `<-o>/miRge.<YYYY-MM-DD_HH-MM-SS>/` and table files.  `-pb` (bowtie directory)
 and `-cpu` are accepted and ignored: no bowtie or cutadapt process is started.
-Only the annotate sub-command exists; -gff writes <sample>_isomiRs.gff (mirge_b200/gff.py); -ai / -trf outputs
+Only the annotate sub-command exists; -gff writes <sample>_isomiRs.gff (mirge_b200/gff.py); -ai writes the A-to-I editing report (mirge_b200/a2i.py); -trf outputs
 are not produced (DESIGN.md "Out of scope").
 """
 import argparse
@@ -88,7 +88,7 @@ def main(argv=None):
         adapter = 'TGGAATTCTCGGGTGCCAAGGAACTCCAG'      # __main__.py:124-125
     elif adapter == 'ion':
         adapter = '11'                                  # __main__.py:126-127 (cutadapt rejects it: starts with a digit)
-    for flag, name in ((args.a_to_i, '-ai'), (args.trf_output, '-trf')):
+    for flag, name in ((args.trf_output, '-trf'),):
         if flag:
             print('warning: %s output is not produced by this build' % name, file=sys.stderr)
 
@@ -120,6 +120,8 @@ def main(argv=None):
     try:
         run = AnnotateRun(samples, args.libraryPath, args.species, db, adapter, args.spikeIn,
                           max_unique=args.max_unique, device=device, log=log, rank=rank, world=world)
+        if args.a_to_i and not os.path.isfile(run.libdir.genome_base + '.fa'):
+            raise LibraryError('%s.fa does not exist: -ai needs the genome.' % run.libdir.genome_base)
         if args.gff_output and not os.path.isfile(run.libdir.gff3):     # extractPreMiRName opens it unguarded (IOError upstream)
             raise LibraryError('%s does not exist: -gff needs the miRNA coordinate file.' % run.libdir.gff3)
         if rank == 0:
@@ -127,7 +129,7 @@ def main(argv=None):
         run.run()
         t1 = time.time()
         log('Summarizing and tabulating results...')
-        run.write_outputs(outdir, args.canoRatio, tcf=args.trimmed_collapsed_fa, isomir_diff=args.diff_isomirs, gff=args.gff_output)
+        run.write_outputs(outdir, args.canoRatio, tcf=args.trimmed_collapsed_fa, isomir_diff=args.diff_isomirs, gff=args.gff_output, a_to_i=args.a_to_i)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()

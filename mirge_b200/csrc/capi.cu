@@ -25,14 +25,14 @@
 enum KernelId {
     KID_K0_COUNT = 0, KID_K0_SCAN, KID_K0_LINES,          // 0..2: retired (round 1's three-pass K0)
     KID_K0_PACK, KID_K1_TRIM, KID_K3_KEYS, KID_K3_SORT,
-    KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_RESET, KID_GENOME,
+    KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_RESET, KID_GENOME, KID_IMPORT,
     KID_K2_ROUND0 = 16,   // .. KID_K2_ROUND0 + 9
     KID_K1_CLASSIFY = 26, KID_K1_SCAN, KID_K1_GENERAL, KID_K1_SLOW,
     KID_N = 30
 };
 static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
     "", "", "", "k0_parse_pack", "k1_trim_collapse", "k3_make_keys",
-    "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "reset_memset", "k2g_genome_all_hits", "",
+    "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "reset_memset", "k2g_genome_all_hits", "exchange_import",
     "k2_round0_mirna_exact", "k2_round1_hairpin", "k2_round2_mature_trna", "k2_round3_pre_trna", "k2_round4_snorna",
     "k2_round5_rrna", "k2_round6_ncrna_others", "k2_round7_mrna", "k2_round8_isomir", "k2_round9_spikein",
     "k1a_classify_collapse", "k1b_scan_class1", "k1c_general_search", "k1d_slow_search", "", ""};
@@ -1041,7 +1041,7 @@ int mirge_import_records_device(mirge_ctx *ctx, const void *dev_buf, uint64_t n_
     if (n_records == 0) return MIRGE_OK;
     CK(cudaSetDevice(ctx->device));
     const int rb = mirge_record_bytes(ctx), g = grid_for(n_records, 128, 148 * 8);
-    ProfScope ps(ctx, KID_EXCHANGE);
+    ProfScope ps(ctx, KID_IMPORT);
     if (ctx->W == 2) k1_import_records<2><<<g, 128, 0, ctx->stream>>>((const unsigned char *)dev_buf, n_records, rb, table_view<2>(ctx));
     else k1_import_records<4><<<g, 128, 0, ctx->stream>>>((const unsigned char *)dev_buf, n_records, rb, table_view<4>(ctx));
     CK(cudaGetLastError());

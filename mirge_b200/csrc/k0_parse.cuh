@@ -403,12 +403,12 @@ __device__ __forceinline__ void k0_pack_pass(const unsigned char *__restrict__ t
 }
 
 // Does the tile's newline with list index li end a well-formed record?  (first-record test of the claim)
-__device__ __forceinline__ u32 k0_test_candidate(const unsigned char *buf, const u16 *lst, u32 li)
+__device__ __forceinline__ u32 k0_test_candidate(const unsigned char *buf, const u16 *lst, u32 li, bool chunk_start)
 {
     u32 l[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) l[k] = lst[li - 4 + k];
-    if (l[0] == K0_NONE) return 2u;                  // cannot tell inside the halo
+    if (l[0] == K0_NONE) return chunk_start ? 0u : 2u;   // fewer than four lines before it in the chunk: no record end; else cannot tell inside the halo
     if (buf[l[0]] != '@' || buf[l[2]] != '+') return 0u;
     int sl = (int)(l[2] - 1 - l[1]), ql = (int)(l[4] - 1 - l[3]);
     while (sl > 0 && buf[l[1] + sl - 1] == '\r') sl--;
@@ -454,7 +454,7 @@ k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
             __syncthreads();
             if (pass_lo == 0) {
                 if (tid < 32) {                              // the claim: first of the first four newlines that ends a record
-                    const u32 r = (tid < 4 && tid < T) ? k0_test_candidate(buf, lst, tid + 4) : 0u;
+                    const u32 r = (tid < 4 && tid < T) ? k0_test_candidate(buf, lst, tid + 4, tile_start == 0) : 0u;
                     const unsigned okm = __ballot_sync(0xffffffffu, r == 1u), unk = __ballot_sync(0xffffffffu, r == 2u);
                     u32 claim = okm ? (u32)(__ffs(okm) - 1) : K0_CLAIM_NONE;
                     if (unk && (!okm || (u32)(__ffs(unk) - 1) < claim)) claim = K0_CLAIM_UNDECIDED;

@@ -52,6 +52,9 @@ class LibraryDir:
         self.mirna_fa = os.path.join(library_path, species, 'fasta.Libs', '%s_mirna_SNP_pseudo_%s.fa' % (species, db))
         self.merges_csv = os.path.join(library_path, species, 'annotation.Libs', '%s_merges_%s.csv' % (species, db))
         self.gff3 = os.path.join(library_path, species, 'annotation.Libs', '%s_%s.gff3' % (species, db))     # __main__.py:150
+        self.repetitive_csv = os.path.join(library_path, species, 'annotation.Libs',
+                                           '%s_miRNAs_in_repetitive_element_%s.csv' % (species, db))          # __main__.py:137
+        self.genome_base = os.path.join(self.index_path, '%s_genome' % species)                               # __main__.py:270
         self.types = list(REQUIRED) + (['spike-in'] if spike_in else [])
 
     def index_base(self, t):
@@ -70,6 +73,45 @@ class LibraryDir:
             raise LibraryError('%s is missing: the CUDA mapper reads reference sequences from a FASTA next to each bowtie '
                                'index; create it with `bowtie-inspect %s > %s`.' % (fa, self.index_base(t), fa))
         return read_fasta(fa)
+
+    def load_genome(self):
+        """Chromosomes of index.Libs/<sp>_genome (the -ai genome passes, writeDataToCSV.py:1260,1488)."""
+        fa = self.genome_base + '.fa'
+        if not os.path.isfile(fa):
+            raise LibraryError('%s is missing: -ai maps reads against the genome; create it with `bowtie-inspect %s > %s`.'
+                               % (fa, self.genome_base, fa))
+        return read_fasta(fa)
+
+    def mature_sequences(self):
+        """mirNameSeqDic: name -> sequence from fasta.Libs/<sp>_mirna_SNP_pseudo_<DB>.fa (miRNAmerge.py:4-11)."""
+        out = {}
+        with open(self.mirna_fa) as f:
+            line = f.readline()
+            while line != '':
+                name = line.strip()[1:]
+                out[name] = f.readline().strip()
+                line = f.readline()
+        return out
+
+    def merged_names(self):
+        """mirMergedNameDic: member name -> merged name (__main__.py:114-120)."""
+        out = {}
+        for line in self.merge_lines() or []:
+            c = line.strip().split(',')
+            for item in c[1:]:
+                out[item] = c[0]
+        return out
+
+    def repetitive_mirnas(self):
+        """removedMiRNA_ai_List (__main__.py:138-144); a missing file means none."""
+        out = []
+        if os.path.isfile(self.repetitive_csv):
+            with open(self.repetitive_csv) as f:
+                for line in f:
+                    k = line.strip().split(',')[0]
+                    if k not in out:
+                        out.append(k)
+        return out
 
     def merge_lines(self):
         """Rows of <sp>_merges_<DB>.csv; a missing file skips the merge (miRNAmerge.py:13,42-43)."""

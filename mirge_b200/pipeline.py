@@ -12,6 +12,7 @@ import time
 
 import numpy as np
 
+from . import a2i as a2i_mod
 from . import gff as gff_mod
 from . import tables
 from .engine import Engine, LIB_IDS, MirgeError
@@ -274,7 +275,7 @@ class AnnotateRun:
         return {k: np.concatenate([p[k] for p in parts]) for k in uniq}
 
     # -- outputs ------------------------------------------------------------------
-    def write_outputs(self, outdir, cano_ratio='0.1', tcf=False, isomir_diff=False, gff=False):
+    def write_outputs(self, outdir, cano_ratio='0.1', tcf=False, isomir_diff=False, gff=False, a_to_i=False):
         """summarize -> miRNAmerge -> filter -> generateReport / writeDataToCSV (__main__.py:381-389)."""
         e = self.engine
         uniq = self.gather_unique()
@@ -309,4 +310,23 @@ class AnnotateRun:
             hp_names, hp_seqs = self.libdir.load('hairpin')
             recs = gff_mod.gff_rows(uniq, mir_names, mir_seqs, hp_names, hp_seqs, pre_of, self.libdir.db)
             gff_mod.write_gff(outdir, recs, self.sample_names, self.libdir.db)
+        if a_to_i:  # writeDataToCSV.py:1222-1615
+            self.write_a2i(outdir, uniq, logDic, mirDic)
         return dict(logDic=logDic, mirDic=mirDic, len_hist=t['len_hist'])
+
+    def write_a2i(self, outdir, uniq, logDic, mirDic):
+        """-ai: A-to-I editing report; the two genome bowtie runs become GPU genome passes (csrc/k2_genome.cuh)."""
+        e = self.engine
+        if 8 not in e.lib_names:
+            e.load_genome(*self.libdir.load_genome())
+        names = e.lib_names[0]
+        items = []
+        for s, c, ro, rf in zip(uniq['seq'], uniq['counts'], uniq['round_of'], uniq['ref_of']):
+            if ro == 1 or ro == 9:
+                items.append((s.decode(), names[rf] if ro == 1 else '', names[rf] if ro == 9 else '', [int(x) for x in c]))
+
+        def genome_pass(seqs, n):
+            return e.genome_pass(seqs, 0, n, 28, 2)            # bowtie genome -n <n> -f -a -3 2
+
+        return a2i_mod.write_a2i(outdir, items, self.sample_names, logDic, mirDic, self.libdir.mature_sequences(),
+                                 self.libdir.merged_names(), self.libdir.repetitive_mirnas(), genome_pass, self.log)

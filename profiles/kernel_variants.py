@@ -50,3 +50,22 @@ for mode in K2MODES:
     eng.profile_enable(False)
     d = {n: round(v[0] / max(1, v[1]), 3) for n, v in prof.items() if n.startswith('k2') and v[1] > 0}
     print(hex(mode), 'K2 total', round(sum(d.values()), 3), d, flush=True)
+
+# exchange kernels on one GPU: export for 2 owners, reset, import everything back (argv[4] = 1)
+if len(sys.argv) > 4 and int(sys.argv[4]):
+    eng.set_trim_mode(0)
+    for it in range(3):
+        eng.reset()
+        eng.feed_fastq_device(0, dev_text.data_ptr(), n_reads * rec, 33)
+        eng.sync()
+        if it == 1:
+            eng.profile_enable(True)
+        p, k, U = eng.stats()
+        buf = torch.empty(U * eng.record_bytes(), dtype=torch.uint8, device='cuda')
+        pc = eng.export_records_device(2, buf.data_ptr(), U)
+        eng.reset_unique()
+        eng.import_records_device(buf.data_ptr(), int(pc.sum()))
+        eng.sync()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    print('exchange', {n: round(v[0] / max(1, v[1]), 3) for n, v in prof.items() if n.startswith(('exchange', 'reset')) and v[1] > 0}, 'U', U, flush=True)

@@ -146,11 +146,48 @@ class World:
             open(os.path.join(d, 'index.Libs', base + '.1.ebwt'), 'w').close()
         with open(os.path.join(d, 'fasta.Libs', f'{sp}_mirna_SNP_pseudo_{db}.fa'), 'w') as f:
             f.write(''.join(f'>{n}\n{s}\n' for n, s in zip(self.libs['mirna'][0], self.mature_seqs)))
+            mature_of = dict(zip(self.libs['mirna'][0], self.mature_seqs))
+            for m in self.merges:                      # merged names carry the sequence of their first member
+                c = m.split(',')
+                f.write(f'>{c[0]}\n{mature_of[c[1]]}\n')
         with open(os.path.join(d, 'annotation.Libs', f'{sp}_merges_{db}.csv'), 'w') as f:
             f.write(''.join(m + '\n' for m in self.merges))
         with open(os.path.join(d, 'annotation.Libs', f'{sp}_{db}.gff3'), 'w') as f:
             f.write(self.gff3_text())
         return root
+
+    def genome(self, total=400_000, n_chrom=4, seed=77):
+        """Synthetic genome for the genome passes (library slot 8): n_chrom random chromosomes of `total` bases in all
+        with every hairpin planted once (its miRNA reads then map to one locus) and a few hairpins planted twice on
+        different chromosomes (multi-mappers the A-to-I filter must drop)."""
+        rng = np.random.Generator(np.random.PCG64(seed))
+        hp = self.libs['hairpin'][1]
+        per = max(total // n_chrom, 4 * sum(len(h) for h in hp) // n_chrom + 1000)
+        lut = np.frombuffer(b'ACGT', dtype=np.uint8)
+        chroms = [lut[rng.integers(0, 4, per, dtype=np.uint8)].copy() for _ in range(n_chrom)]
+        slots = [per // (len(hp) // n_chrom + 2)] * n_chrom
+        cursor = [200] * n_chrom
+        twice = set(int(x) for x in rng.choice(len(hp), max(1, len(hp) // 50), replace=False))
+        for k, h in enumerate(hp):
+            for c in ([k % n_chrom, (k + 1) % n_chrom] if k in twice else [k % n_chrom]):
+                a = cursor[c] + int(rng.integers(0, max(1, slots[c] - len(h) - 100)))
+                if a + len(h) + 100 < per:
+                    chroms[c][a:a + len(h)] = np.frombuffer(h.encode(), dtype=np.uint8)
+                cursor[c] = min(per - 200, cursor[c] + slots[c])
+        return ['chr%d' % (c + 1) for c in range(n_chrom)], [c.tobytes().decode() for c in chroms]
+
+    def write_genome(self, root, total=400_000, n_chrom=4, seed=77):
+        """index.Libs/<sp>_genome.fa (+ the .1.ebwt presence marker) and an empty repetitive-element list."""
+        sp, db = self.species, self.db
+        d = os.path.join(root, sp)
+        names, seqs = self.genome(total, n_chrom, seed)
+        with open(os.path.join(d, 'index.Libs', f'{sp}_genome.fa'), 'w') as f:
+            for n, s_ in zip(names, seqs):
+                f.write(f'>{n}\n{s_}\n')
+        open(os.path.join(d, 'index.Libs', f'{sp}_genome.1.ebwt'), 'w').close()
+        with open(os.path.join(d, 'annotation.Libs', f'{sp}_miRNAs_in_repetitive_element_{db}.csv'), 'w') as f:
+            f.write('')
+        return names, seqs
 
     def gff3_text(self):
         """<sp>_<DB>.gff3 in miRBase layout: one miRNA_primary_transcript per hairpin, one miRNA per mature."""

@@ -47,7 +47,7 @@ def test_cli_on_n_ranks_equals_one_rank(tmp_path):
         pytest.skip('needs at least two GPUs (gpurun --gpus 2)')
     n = min(n, 4)
     from synth.world import World
-    w = World(seed=20180626, scale=0.05)
+    w = World(seed=20180626, scale=0.05, snpc_names=True)      # the naming -gff expects next to .SNP entries
     libdir = tmp_path / 'libs'
     w.write(str(libdir))
     s1, s2 = tmp_path / 'a.fastq', tmp_path / 'b.fastq.gz'
