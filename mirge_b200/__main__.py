@@ -120,8 +120,9 @@ def main(argv=None):
     try:
         run = AnnotateRun(samples, args.libraryPath, args.species, db, adapter, args.spikeIn,
                           max_unique=args.max_unique, device=device, log=log, rank=rank, world=world)
-        if args.a_to_i and not os.path.isfile(run.libdir.genome_base + '.fa'):
-            raise LibraryError('%s.fa does not exist: -ai needs the genome.' % run.libdir.genome_base)
+        if args.a_to_i and not run.libdir.has_genome():
+            raise LibraryError('The bowtie index file of %s_genome.*.ebwt is not located at %s, please check it (-ai needs the genome).'
+                               % (args.species, run.libdir.index_path))
         if args.gff_output and not os.path.isfile(run.libdir.gff3):     # extractPreMiRName opens it unguarded (IOError upstream)
             raise LibraryError('%s does not exist: -gff needs the miRNA coordinate file.' % run.libdir.gff3)
         if rank == 0:

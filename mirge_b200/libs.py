@@ -7,13 +7,17 @@
     <lib>/<species>/annotation.Libs/<sp>_<DB>.gff3                  (-gff only)
 
 The reference hands the `.ebwt` indexes to bowtie.  The CUDA mapper needs the
-reference sequences themselves, so next to every index it expects
-`<index>.fa` -- exactly what `bowtie-inspect <index> > <index>.fa` prints
-(the reference itself calls bowtie-inspect at utils/summarize.py:6 and
-utils/runAnnotationPipeline.py:610-611).  The presence check on `.1.ebwt`
-(:262-267) and its message are kept.
+reference names and sequences themselves (the reference gets them from
+bowtie-inspect at utils/summarize.py:6 and utils/runAnnotationPipeline.py:610-611):
+they are read straight from the index files (`.1.ebwt` names, `.3.ebwt`/`.4.ebwt`
+2-bit reference; mirge_b200/ebwt.py), unless `<index>.fa` -- what
+`bowtie-inspect <index> > <index>.fa` prints -- lies next to the index, which
+takes precedence.  The presence check on `.1.ebwt` (:262-267) and its message
+are kept.
 """
 import os
+
+from . import ebwt
 
 LIB_TYPES = {            # library slot -> index basename suffix
     'mirna': 'mirna_%(db)s', 'hairpin': 'hairpin_%(db)s', 'mrna': 'mrna', 'mature_trna': 'mature_trna',
@@ -67,20 +71,27 @@ class LibraryDir:
                 raise LibraryError('The bowtie index file of %s_%s.*.ebwt is not located at %s, please check it.'
                                    % (self.species, LIB_TYPES[t] % {'db': self.db}, self.index_path))
 
+    @staticmethod
+    def _load_base(base, what):
+        if os.path.isfile(base + '.fa'):
+            return read_fasta(base + '.fa')
+        if ebwt.has_sequences(base):
+            try:
+                return ebwt.read_index(base)
+            except ebwt.EbwtError as e:
+                raise LibraryError('%s; `bowtie-inspect %s > %s.fa` next to the index is read instead when present.' % (e, base, base))
+        raise LibraryError('%s: neither %s.fa nor readable %s.{1,3,4}.ebwt files were found; create the FASTA with '
+                           '`bowtie-inspect %s > %s.fa`.' % (what, base, base, base, base))
+
     def load(self, t):
-        fa = self.index_base(t) + '.fa'
-        if not os.path.isfile(fa):
-            raise LibraryError('%s is missing: the CUDA mapper reads reference sequences from a FASTA next to each bowtie '
-                               'index; create it with `bowtie-inspect %s > %s`.' % (fa, self.index_base(t), fa))
-        return read_fasta(fa)
+        return self._load_base(self.index_base(t), 'library %s' % t)
+
+    def has_genome(self):
+        return os.path.isfile(self.genome_base + '.fa') or ebwt.has_sequences(self.genome_base)
 
     def load_genome(self):
         """Chromosomes of index.Libs/<sp>_genome (the -ai genome passes, writeDataToCSV.py:1260,1488)."""
-        fa = self.genome_base + '.fa'
-        if not os.path.isfile(fa):
-            raise LibraryError('%s is missing: -ai maps reads against the genome; create it with `bowtie-inspect %s > %s`.'
-                               % (fa, self.genome_base, fa))
-        return read_fasta(fa)
+        return self._load_base(self.genome_base, 'the genome (-ai)')
 
     def mature_sequences(self):
         """mirNameSeqDic: name -> sequence from fasta.Libs/<sp>_mirna_SNP_pseudo_<DB>.fa (miRNAmerge.py:4-11)."""

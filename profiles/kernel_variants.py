@@ -12,7 +12,7 @@ import torch
 from synth.world import World
 from mirge_b200.engine import Engine
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 25_000_000
-modes = [int(x, 0) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 0x800, 0x100, 0x200, 4]
+modes = [int(x, 0) for x in sys.argv[2].split(',') if x] if len(sys.argv) > 2 else [0, 0x800, 0x100, 0x200, 4]
 world = World(seed=20180626, scale=1.0)
 rec = world.record_bytes(50)
 host = torch.empty(n_reads * rec, dtype=torch.uint8, pin_memory=True)
@@ -32,11 +32,12 @@ for mode in modes:
     eng.profile_enable(False)
     p, k, U = eng.stats()
     print(hex(mode), 'kept', int(k[0]), 'U', U, {n: round(v[0] / max(1, v[1]), 3) for n, v in prof.items() if n.startswith('k1') and v[1] > 0}, flush=True)
-K2MODES = [int(x, 0) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else []
+K2MODES = [int(x, 0) for x in sys.argv[3].split(",") if x] if len(sys.argv) > 3 else []
 # K2 variants (needs libraries)
 from mirge_b200.engine import LIB_IDS
-for t, i in LIB_IDS.items():
-    eng.load_library(i, *world.libs[t])
+if K2MODES:
+    for t, i in LIB_IDS.items():
+        eng.load_library(i, *world.libs[t])
 for mode in K2MODES:
     eng.set_trim_mode(mode)
     for it in range(3):
