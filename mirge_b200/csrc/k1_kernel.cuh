@@ -398,22 +398,90 @@ __device__ __forceinline__ u32 k1_finish_warp(PSeq<W> &p, int n, bool on, int mi
 }
 
 // ---------------------------------------------------------------------------
-// K1 is a short pipeline of four kernels, each one homogeneous (small code, full
+// K1 is a short pipeline of three kernels, each one homogeneous (small code, full
 // warps, its own occupancy):
-//   k1_trim_collapse  every read: prefilter; class 0 -> length filter + upsert;
-//                     class 1 / 2 -> appended to device queues
-//   k1_scan_class1    queue 1: full-candidate cost scan; clean -> upsert, else queue 2
+//   k1_trim_collapse  every read: prefilter; class 0 -> length filter + upsert; class 1 -> the
+//                     pigeonhole filter (k1_piece_hit) settles it on the spot or makes it class 2;
+//                     class 2 -> appended to queue 2
 //   k1_general_search queue 2: windowed bit-vector search with candidate walks;
 //                     unsettled -> queue 3
 //   k1_slow_search    queue 3: all-column search (or the literal DP)
-// Queue appends are warp-aggregated (one atomic per warp and queue).
+// Queue entries are the quality-trimmed reads themselves (one 32-byte record at W = 2), written
+// and read coalesced: the queue kernels never go back to the K0 record arrays.  Appends are
+// warp-aggregated (chunk reservation, one atomic per 32 entries).
 // ---------------------------------------------------------------------------
+template <int W> struct K1QRec;
+template <> struct alignas(32) K1QRec<2> { u64 s[2]; u64 nm[1]; u32 n; u32 pad; };
+template <> struct alignas(64) K1QRec<4> { u64 s[4]; u64 nm[2]; u32 n; u32 pad; u64 pad2; };
+#define K1Q_NONE 0xFFFFFFFFu      // n of a padding entry
+#define K1Q_CHUNK 32
+
 struct K1Queues {
-    u64 *n;           // [3] fills of q1, q2, q3
-    u64 *q1;          // record index | (rstart | limit << 8) << 32
-    u32 *q2;
-    u32 *q3;
+    u64 *n;           // [2] fills of q2, q3
+    void *q2;         // K1QRec<W>[]
+    void *q3;
 };
+
+// warp-aggregated append of whole records (common.cuh:warpq_slot hands out the slots)
+template <int W>
+__device__ __forceinline__ void k1q_push(bool push, u64 *fill, K1QRec<W> *q, WarpQ &wq, const PSeq<W> &p, int n)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned b = __ballot_sync(0xffffffffu, push);
+    const u32 c = __popc(b);
+    if (!c) return;
+    const u32 rank = __popc(b & ((1u << lane) - 1u));
+    u64 slot;
+    if (c <= wq.left) {
+        slot = wq.pos + rank;
+        wq.pos += c; wq.left -= c;
+    } else {
+        u64 nb = 0;
+        if (lane == 0) nb = atomicAdd(fill, (u64)K1Q_CHUNK);
+        nb = __shfl_sync(0xffffffffu, nb, 0);
+        const u32 spill = c - wq.left;
+        slot = rank < wq.left ? wq.pos + rank : nb + (rank - wq.left);
+        wq.pos = nb + spill; wq.left = K1Q_CHUNK - spill;
+    }
+    if (push) {
+        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(q + slot);
+        if (W == 2) {
+            d[0] = make_ulonglong2(p.s[0], p.s[1]);
+            d[1] = make_ulonglong2(p.nm[0], (u64)(u32)n);
+        } else {
+            d[0] = make_ulonglong2(p.s[0], p.s[1]);
+            d[1] = make_ulonglong2(p.s[W - 2], p.s[W - 1]);
+            d[2] = make_ulonglong2(p.nm[0], p.nm[W / 2 - 1]);
+            d[3] = make_ulonglong2((u64)(u32)n, 0ull);
+        }
+    }
+}
+template <int W>
+__device__ __forceinline__ void k1q_close(K1QRec<W> *q, const WarpQ &wq)
+{
+    for (u32 x = threadIdx.x & 31; x < wq.left; x += 32) q[wq.pos + x].n = K1Q_NONE;
+}
+template <int W>
+__device__ __forceinline__ bool k1q_load(const K1QRec<W> *q, u64 i, u64 fill, PSeq<W> &p, int &n)
+{
+#pragma unroll
+    for (int w = 0; w < W; w++) p.s[w] = 0;
+#pragma unroll
+    for (int w = 0; w < W / 2; w++) p.nm[w] = 0;
+    n = 0;
+    if (i >= fill) return false;
+    const ulonglong2 *d = reinterpret_cast<const ulonglong2 *>(q + i);
+    if (W == 2) {
+        const ulonglong2 a = d[0], b = d[1];
+        if ((u32)b.y == K1Q_NONE) return false;
+        p.s[0] = a.x; p.s[1] = a.y; p.nm[0] = b.x; n = (int)(u32)b.y;
+    } else {
+        const ulonglong2 a = d[0], b = d[1], c = d[2], e = d[3];
+        if ((u32)e.x == K1Q_NONE) return false;
+        p.s[0] = a.x; p.s[1] = a.y; p.s[W - 2] = b.x; p.s[W - 1] = b.y; p.nm[0] = c.x; p.nm[W / 2 - 1] = c.y; n = (int)(u32)e.x;
+    }
+    return true;
+}
 
 struct K1Shared {
     TrimParams tp;                                  // dynamic indexing by adapter: keep it out of local memory
@@ -460,12 +528,13 @@ __device__ __forceinline__ void k1_teardown(u32 my_kept, u32 my_diag, u64 *diag,
 template <int W>
 __global__ void __launch_bounds__(K1A_THREADS)
 k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-                 const u64 *__restrict__ n_records_ptr, int sample, TrimParams tp_param, K1Pre pre_param, TableView<W> T, K1Counters ctr, K1Queues Q,
-                 int force_slow)
+                 const u64 *__restrict__ n_records_ptr, int sample, TrimParams tp_param, K1Pre pre_param, K1Thr thr_param,
+                 TableView<W> T, K1Counters ctr, K1Queues Q, int force_slow)
 {
     __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ u32 sh_cid[K1_CC * (K1A_THREADS / 32)], sh_ccnt[K1_CC * (K1A_THREADS / 32)];
     __shared__ K1Pre pre;
+    __shared__ u64 sh_bm[4 * W * K1A_THREADS];           // base-position masks of the pigeonhole filter
     for (int b = threadIdx.x; b < K1_HIST(W); b += K1A_THREADS) sh_hist[b] = 0;
     for (int b = threadIdx.x; b < K1_CC * (K1A_THREADS / 32); b += K1A_THREADS) { sh_cid[b] = 0xFFFFFFFFu; sh_ccnt[b] = 0; }
     u32 *wh = sh_hist;
@@ -477,8 +546,10 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
     const bool use_pre = pre.enabled && !(force_slow & 4);
     const int mode = tp_param.mode, uncond = tp_param.uncond, min_length = tp_param.min_length;
     const u64 aw0 = tp_param.aw[0][0];
-    u32 my_kept = 0;
-    WarpQ wq1 = {0, 0}, wq2 = {0, 0}, wq3 = {0, 0};
+    const int m0 = tp_param.alen[0], kmax0 = m0 <= MIRGE_MAX_ADAPTER_LEN ? thr_param.v[m0] : -1;
+    K1QRec<W> *q2 = reinterpret_cast<K1QRec<W> *>(Q.q2), *q3 = reinterpret_cast<K1QRec<W> *>(Q.q3);
+    u32 my_kept = 0, my_c1 = 0;
+    WarpQ wq2 = {0, 0}, wq3 = {0, 0};
     for (u64 r0 = (u64)blockIdx.x * K1A_THREADS; r0 < n_records; r0 += (u64)gridDim.x * K1A_THREADS) {
         const u64 r = r0 + threadIdx.x;
         const bool live = r < n_records;
@@ -501,12 +572,12 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
             else cls = 2;
         }
         if (!live) cls = -1;
-        const u64 s1 = warpq_slot(cls == 1, Q.n + 0, Q.q1, wq1);
-        const u64 s2 = warpq_slot(cls == 2, Q.n + 1, Q.q2, wq2);
-        const u64 s3 = warpq_slot(cls == 3, Q.n + 2, Q.q3, wq3);
-        if (cls == 1) Q.q1[s1] = r | ((u64)(nf | (lim << 8)) << 32);
-        else if (cls == 2) Q.q2[s2] = (u32)r;
-        else if (cls == 3) Q.q3[s3] = (u32)r;
+        if (cls == 1) {
+            my_c1++;
+            cls = k1_piece_hit<W>(p, lim, m0, kmax0, aw0, sh_bm + threadIdx.x, K1A_THREADS) ? 2 : 0;
+        }
+        k1q_push<W>(cls == 2, Q.n + 0, q2, wq2, p, n);
+        k1q_push<W>(cls == 3, Q.n + 1, q3, wq3, p, n);
         const bool keep = cls == 0 && nf >= min_length;
         if (force_slow & 0x200) { my_kept += keep; continue; }             // diagnostic: classification only
         if (keep) pseq_truncate<W>(p, nf);
@@ -518,55 +589,13 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
         if (keep) { atomicAdd(&wh[nf], 1u); my_kept++; }
     }
     count_cache_flush<W>(cid, ccnt, T, sample);
-    warpq_close(Q.q1, wq1); warpq_close(Q.q2, wq2); warpq_close(Q.q3, wq3);
-    k1_teardown<W>(my_kept, 0u, nullptr, sh_hist, ctr, T.S, sample);
+    k1q_close<W>(q2, wq2); k1q_close<W>(q3, wq3);
+    k1_teardown<W>(my_kept, my_c1, ctr.slow_reads ? ctr.slow_reads + 1 : nullptr, sh_hist, ctr, T.S, sample);
 }
 
 template <int W>
 __global__ void __launch_bounds__(K1_THREADS)
-k1_scan_class1(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-               int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q)
-{
-    __shared__ u32 sh_hist[K1_HIST(W)];
-    __shared__ u32 peq8[8];
-    for (int b = threadIdx.x; b < K1_HIST(W); b += K1_THREADS) sh_hist[b] = 0;
-    u32 *wh = sh_hist;
-    if (threadIdx.x < 8) peq8[threadIdx.x] = (threadIdx.x & 4) ? 0u : (u32)tp_param.peq[0][threadIdx.x & 3];
-    __syncthreads();
-    const u64 n1 = *Q.n;
-    const int m = tp_param.alen[0], thr_m = thr_param.v[m], min_length = tp_param.min_length;
-    u32 my_kept = 0, my_n = 0;
-    WarpQ wq2 = {0, 0};
-    for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n1; i0 += (u64)gridDim.x * K1_THREADS) {
-        const u64 i = i0 + threadIdx.x;
-        const u64 e = i < n1 ? Q.q1[i] : ~0ull;
-        const bool on = e != ~0ull;
-        PSeq<W> ps;
-        int ns = 0, lim = 0, rs = 0;
-        u32 rr = 0;
-        if (on) {
-            rr = (u32)e; rs = (int)((e >> 32) & 0xFF); lim = (int)(e >> 40);
-            k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
-            my_n++;
-        } else {
-#pragma unroll
-            for (int w = 0; w < W; w++) ps.s[w] = 0;
-#pragma unroll
-            for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
-        }
-        const bool hit = k1_full_candidate_scan<W>(ps, lim, m, thr_m, peq8);
-        const u64 s2 = warpq_slot(on && hit, Q.n + 1, Q.q2, wq2);   // a full-length candidate: the general search decides
-        if (on && hit) Q.q2[s2] = rr;
-        my_kept += k1_finish_warp<W>(ps, rs, on && !hit, min_length, T, sample, wh);
-    }
-    warpq_close(Q.q2, wq2);
-    k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 1 : nullptr, sh_hist, ctr, T.S, sample);
-}
-
-template <int W>
-__global__ void __launch_bounds__(K1_THREADS)
-k1_general_search(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-                  int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q)
+k1_general_search(int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q)
 {
     __shared__ u64 ring[K1_RING * K1_THREADS];
     __shared__ u32 ringh[K1_RING * K1_THREADS];
@@ -574,59 +603,42 @@ k1_general_search(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, 
     __shared__ K1Shared sh;
     k1_setup<W>(sh, sh_hist, tp_param, thr_param);
     u32 *wh = sh_hist;
-    const u64 n2 = Q.n[1];
+    const u64 n2 = Q.n[0];
+    const K1QRec<W> *q2 = reinterpret_cast<const K1QRec<W> *>(Q.q2);
+    K1QRec<W> *q3 = reinterpret_cast<K1QRec<W> *>(Q.q3);
     u32 my_kept = 0, my_n = 0;
     WarpQ wq3 = {0, 0};
     for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n2; i0 += (u64)gridDim.x * K1_THREADS) {
-        const u64 i = i0 + threadIdx.x;
-        const u32 rr = i < n2 ? Q.q2[i] : WARPQ_NONE;
-        const bool on = rr != WARPQ_NONE;
         PSeq<W> ps;
         int ns = 0;
-        if (on) {
-            k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
-            my_n++;
-        } else {
-#pragma unroll
-            for (int w = 0; w < W; w++) ps.s[w] = 0;
-#pragma unroll
-            for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
-        }
+        const bool on = k1q_load<W>(q2, i0 + threadIdx.x, n2, ps, ns);
+        my_n += on;
         const int nfs = k1_trim_fast<W>(ps, ns, sh.tp, sh.thr, ring + threadIdx.x, ringh + threadIdx.x, sh.peq8);   // warp-collective
-        const u64 s3 = warpq_slot(on && nfs == K1_SLOW, Q.n + 2, Q.q3, wq3);
-        if (on && nfs == K1_SLOW) Q.q3[s3] = rr;
+        k1q_push<W>(on && nfs == K1_SLOW, Q.n + 1, q3, wq3, ps, ns);
         my_kept += k1_finish_warp<W>(ps, nfs, on && nfs != K1_SLOW, sh.tp.min_length, T, sample, wh);
     }
-    warpq_close(Q.q3, wq3);
+    k1q_close<W>(q3, wq3);
     k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 2 : nullptr, sh_hist, ctr, T.S, sample);
 }
 
 template <int W>
 __global__ void __launch_bounds__(K1_THREADS)
-k1_slow_search(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
-               int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q, int literal)
+k1_slow_search(int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q, int literal)
 {
     __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ K1Shared sh;
     k1_setup<W>(sh, sh_hist, tp_param, thr_param);
     u32 *wh = sh_hist;
-    const u64 n3 = Q.n[2];
+    const u64 n3 = Q.n[1];
+    const K1QRec<W> *q3 = reinterpret_cast<const K1QRec<W> *>(Q.q3);
     u32 my_kept = 0, my_n = 0;
     for (u64 i0 = (u64)blockIdx.x * K1_THREADS; i0 < n3; i0 += (u64)gridDim.x * K1_THREADS) {
-        const u64 i = i0 + threadIdx.x;
-        const u32 rr = i < n3 ? Q.q3[i] : WARPQ_NONE;
-        const bool on = rr != WARPQ_NONE;
         PSeq<W> ps;
         int ns = 0, nfs = 0;
+        const bool on = k1q_load<W>(q3, i0 + threadIdx.x, n3, ps, ns);
         if (on) {
-            k1_load_record<W>(bases, nmask, meta, (u64)rr, ps, ns);
             nfs = k1_trim_slow<W>(ps, ns, sh.tp, sh.thr, sh.peq8, literal != 0);
             my_n++;
-        } else {
-#pragma unroll
-            for (int w = 0; w < W; w++) ps.s[w] = 0;
-#pragma unroll
-            for (int w = 0; w < W / 2; w++) ps.nm[w] = 0;
         }
         __syncwarp();
         my_kept += k1_finish_warp<W>(ps, nfs, on, sh.tp.min_length, T, sample, wh);

@@ -157,6 +157,59 @@ __host__ __device__ __forceinline__ bool k1_full_candidate_scan(const PSeq<W> &p
     return hit;
 }
 
+// Class 1 without dynamic programming: the pigeonhole filter.  A full-length candidate ending at a column j <= limit
+// is an occurrence of the whole adapter with at most kmax = thr[m] edits (substitutions, insertions, deletions) inside
+// read[0..limit).  Cut the adapter into kmax + 1 disjoint pieces: kmax edits touch at most kmax of them, so at least
+// one piece occurs EXACTLY in read[0..limit).  No piece occurrence there -> no candidate -> E wins.  (The converse does
+// not hold: a hit only sends the read to the general search.)  Piece occurrences are found for all positions at once:
+// per base x a mask of the positions holding x (2-bit words, even bits), then for a piece P
+//     R_len = all positions,   R_u = mask[P[u]] & (R_{u+1} >> one base)        (R_0 = start positions of P)
+// N is packed as A and may only add hits.  bm: this thread's scratch, 4 masks of W words, element (x * W + w) * stride
+// (shared memory on the device: the mask is selected by the adapter base, a run-time index).
+template <int W>
+__host__ __device__ __forceinline__ bool k1_piece_hit(const PSeq<W> &p, int limit, int m, int kmax, u64 aw, u64 *bm, int stride)
+{
+    const u64 M5 = 0x5555555555555555ull;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        const u64 L = p.s[w] & M5, H = (p.s[w] >> 1) & M5;
+        bm[(0 * W + w) * stride] = M5 & ~(L | H);
+        bm[(1 * W + w) * stride] = L & ~H;
+        bm[(2 * W + w) * stride] = H & ~L;
+        bm[(3 * W + w) * stride] = L & H;
+    }
+    const int np = kmax + 1;
+    bool hit = false;
+    for (int q = 0; q < np; q++) {
+        const int b0 = (q * m) / np, b1 = ((q + 1) * m) / np, len = b1 - b0;
+        const int cnt = limit - len + 1;                       // start positions 0 .. limit - len
+        if (cnt <= 0) continue;
+        u64 acc[W];
+        {
+            const int c = (int)((aw >> (2 * (b1 - 1))) & 3ull);
+#pragma unroll
+            for (int w = 0; w < W; w++) acc[w] = bm[(c * W + w) * stride];
+        }
+        for (int t = b1 - 2; t >= b0; t--) {
+            const int c = (int)((aw >> (2 * t)) & 3ull);
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                const u64 up = (w + 1 < W) ? acc[w + 1] << 62 : 0ull;
+                acc[w] = bm[(c * W + w) * stride] & ((acc[w] >> 2) | up);
+            }
+        }
+        u64 any = 0;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const int lo = 32 * w;
+            u64 pm = (cnt <= lo) ? 0ull : (cnt >= lo + 32) ? M5 : (M5 & ((1ull << (2 * (cnt - lo))) - 1ull));
+            any |= acc[w] & pm;
+        }
+        hit = hit || any != 0ull;
+    }
+    return hit;
+}
+
 // Class "1b" (NOT wired into the kernels yet; exercised on the host by tests/test_k1_host_compiled.py): reads that
 // end with an exact adapter prefix of l bases (l >= min_overlap) which the tables cannot settle -- typically a SHORT
 // prefix behind a long insert.  E still wins unless a candidate with more than l matches exists:

@@ -141,7 +141,7 @@ def _decide(host_kernel, pre, adapter, rate, mo, reads, W, use_1b):
 @pytest.mark.parametrize('adapter', [ILLUMINA, 'TGGAATTCTCGGGTGCCAAGG', 'ACACACACACACACACACAC', 'AGATCGGAAGAGCACACGTCTGAACTCCAGTC',
                                      'AACTGTAGGCACCATCAAT', 'TTTTGGAATTTTGGAATTGGAATT'])
 @pytest.mark.parametrize('rate,mo', [(0.12, 3), (0.2, 1)])
-@pytest.mark.parametrize('use_1b', [False, True])
+@pytest.mark.parametrize('use_1b', [0, 1, 2])       # bit 0: the class-1b prefix scan, bit 1: class 1 by the pigeonhole filter (the kernel's way)
 def test_whole_read_decision_matches_oracle(host_kernel, oracle_mod, adapter, rate, mo, use_1b):
     """prefilter -> class 0 / class-1 scan / (planned) class-1b scan -> general -> slow search: the trimmed length every
     path of the K1 pipeline arrives at, device code on the host, against Adapter.match_to."""
@@ -164,7 +164,7 @@ def test_whole_read_decision_matches_oracle(host_kernel, oracle_mod, adapter, ra
             mb = O.match_back(adapter, r, rate, mo)
             assert int(got[k, 0]) == (mb[0] if mb else len(r)), (adapter, r, got[k].tolist(), mb)
         paths.update(got[:, 1].tolist())
-    assert {0, 4} <= paths and (not use_1b or 3 in paths)
+    assert {0, 4} <= paths and 9 not in paths and (not (use_1b & 1) or 3 in paths)
 
 
 def test_whole_read_decision_on_the_bench_workload(host_kernel, oracle_mod, small_world):
@@ -177,7 +177,7 @@ def test_whole_read_decision_on_the_bench_workload(host_kernel, oracle_mod, smal
         st, sp = O.quality_trim_index(q, 0, 10, 33)
         reads.append(seq[st:sp] or 'A')
     share = {}
-    for use_1b in (False, True):
+    for use_1b in (False, True, 2):
         got = _decide(host_kernel, pre, ILLUMINA, 0.12, 3, reads, 2, use_1b)
         for k, r in enumerate(reads):
             mb = O.match_back(ILLUMINA, r, 0.12, 3)
@@ -185,3 +185,4 @@ def test_whole_read_decision_on_the_bench_workload(host_kernel, oracle_mod, smal
         share[use_1b] = np.bincount(got[:, 1], minlength=5) / float(len(reads))
     assert share[False][0] > 0.55 and share[False][4] < 0.15          # what the kernels do today
     assert share[True][4] < 0.07 and share[True][3] > 0.04            # the planned class 1b halves the general search's load
+    assert share[2][2] < 0.01 and share[2][1] > 0.2                   # the pigeonhole filter settles nearly every class-1 read
