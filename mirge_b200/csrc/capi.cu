@@ -891,6 +891,27 @@ int mirge_tally(mirge_ctx *ctx)
 // ---------------------------------------------------------------------------
 // export
 // ---------------------------------------------------------------------------
+// out[u * stride + i] = base i of unique u as ASCII (N for ambiguous), zero beyond its length
+template <int W>
+__global__ void k_unpack_unique(const u64 *__restrict__ useq, const u64 *__restrict__ unmask, const u8 *__restrict__ ulen, u64 U, int stride,
+                                unsigned char *__restrict__ out)
+{
+    const int gpu = (stride + 3) / 4;                       // 4-base groups per unique
+    for (u64 it = (u64)blockIdx.x * blockDim.x + threadIdx.x; it < U * (u64)gpu; it += (u64)gridDim.x * blockDim.x) {
+        const u64 u = it / gpu;
+        const int g = (int)(it % gpu), n = ulen[u];
+        const u32 two = g * 4 < 32 * W ? (u32)((useq[u * W + (g >> 3)] >> ((g & 7) * 8)) & 0xFFull) : 0u;
+        const u32 nb = g * 4 < 32 * W ? (u32)((unmask[u * (W / 2) + (g >> 4)] >> ((g & 15) * 4)) & 0xFull) : 0u;
+        for (int k = 0; k < 4; k++) {
+            const int i = 4 * g + k;
+            if (i >= stride) break;
+            unsigned char c = 0;
+            if (i < n) c = ((nb >> k) & 1u) ? 'N' : "ACGT"[(two >> (2 * k)) & 3u];
+            out[u * (u64)stride + i] = c;
+        }
+    }
+}
+
 int mirge_export_unique(mirge_ctx *ctx, uint64_t cap, int stride, char *seq, uint8_t *len, uint32_t *counts,
                         int8_t *round_of, int32_t *ref_of, int32_t *pos_of, int8_t *mm_of)
 {
@@ -900,23 +921,19 @@ int mirge_export_unique(mirge_ctx *ctx, uint64_t cap, int stride, char *seq, uin
     if (cap < U) return fail(ctx, MIRGE_E_ARG, "mirge_export_unique: capacity smaller than n_unique");
     if (seq && stride < ctx->max_len) return fail(ctx, MIRGE_E_ARG, "mirge_export_unique: stride smaller than max_read_len");
     const int W = ctx->W;
-    std::vector<u8> hl(U);
-    CK(cudaMemcpy(hl.data(), ctx->d_ulen, U, cudaMemcpyDeviceToHost));
-    if (len) memcpy(len, hl.data(), U);
-    if (seq) {
-        std::vector<u64> hs(U * W), hn(U * (W / 2));
-        CK(cudaMemcpy(hs.data(), ctx->d_useq, U * W * sizeof(u64), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(hn.data(), ctx->d_unmask, U * (W / 2) * sizeof(u64), cudaMemcpyDeviceToHost));
-        static const char ACGT[4] = {'A', 'C', 'G', 'T'};
-        for (u64 u = 0; u < U; u++) {
-            char *o = seq + u * (u64)stride;
-            const int n = hl[u];
-            for (int i = 0; i < n; i++) {
-                const int isn = (int)((hn[u * (W / 2) + (i >> 6)] >> (i & 63)) & 1);
-                o[i] = isn ? 'N' : ACGT[(hs[u * W + (i >> 5)] >> ((i & 31) * 2)) & 3];
-            }
-            if (n < stride) memset(o + n, 0, (size_t)(stride - n));
-        }
+    if (len) CK(cudaMemcpy(len, ctx->d_ulen, U, cudaMemcpyDeviceToHost));
+    if (seq && U) {
+        // 2-bit -> ASCII on the device (four bases per thread, coalesced), one copy back
+        unsigned char *d_out = nullptr;
+        CK(cudaMalloc(&d_out, (size_t)U * stride));
+        const u64 items = U * (u64)((stride + 3) / 4);
+        ctx->n_launches++;
+        if (W == 2) k_unpack_unique<2><<<grid_for(items, 256, 148 * 16), 256, 0, ctx->stream>>>(ctx->d_useq, ctx->d_unmask, ctx->d_ulen, U, stride, d_out);
+        else k_unpack_unique<4><<<grid_for(items, 256, 148 * 16), 256, 0, ctx->stream>>>(ctx->d_useq, ctx->d_unmask, ctx->d_ulen, U, stride, d_out);
+        cudaError_t e = cudaMemcpyAsync(seq, d_out, (size_t)U * stride, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_out);
+        if (e != cudaSuccess) { ctx->err = std::string("mirge_export_unique failed: ") + cudaGetErrorString(e); return MIRGE_E_CUDA; }
     }
     if (counts) CK(cudaMemcpy(counts, ctx->d_counts, U * ctx->S * sizeof(u32), cudaMemcpyDeviceToHost));
     if (ctx->annotated) {
@@ -1037,7 +1054,7 @@ int mirge_import_records_device(mirge_ctx *ctx, const void *dev_buf, uint64_t n_
 {
     if (n_records == 0) return MIRGE_OK;
     CK(cudaSetDevice(ctx->device));
-    const int rb = mirge_record_bytes(ctx), g = grid_for(n_records, 128, 148 * 8);
+    const int rb = mirge_record_bytes(ctx), g = grid_for(n_records, 128, 148 * 16);
     ProfScope ps(ctx, KID_IMPORT);
     if (ctx->W == 2) k1_import_records<2><<<g, 128, 0, ctx->stream>>>((const unsigned char *)dev_buf, n_records, rb, table_view<2>(ctx));
     else k1_import_records<4><<<g, 128, 0, ctx->stream>>>((const unsigned char *)dev_buf, n_records, rb, table_view<4>(ctx));

@@ -534,7 +534,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
     __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ u32 sh_cid[K1_CC * (K1A_THREADS / 32)], sh_ccnt[K1_CC * (K1A_THREADS / 32)];
     __shared__ K1Pre pre;
-    __shared__ u64 sh_bm[4 * W * K1A_THREADS];           // base-position masks of the pigeonhole filter
+    __shared__ u64 sh_bm[4 * (W / 2) * K1A_THREADS];     // base-position masks of the pigeonhole filter
     for (int b = threadIdx.x; b < K1_HIST(W); b += K1A_THREADS) sh_hist[b] = 0;
     for (int b = threadIdx.x; b < K1_CC * (K1A_THREADS / 32); b += K1A_THREADS) { sh_cid[b] = 0xFFFFFFFFu; sh_ccnt[b] = 0; }
     u32 *wh = sh_hist;

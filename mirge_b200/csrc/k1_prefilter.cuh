@@ -157,26 +157,41 @@ __host__ __device__ __forceinline__ bool k1_full_candidate_scan(const PSeq<W> &p
     return hit;
 }
 
+// 32 bits -> even bits in the low half, odd bits in the high half (the classic unshuffle)
+__host__ __device__ __forceinline__ u32 deinterleave32(u32 x)
+{
+    u32 t;
+    t = (x ^ (x >> 1)) & 0x22222222u; x ^= t ^ (t << 1);
+    t = (x ^ (x >> 2)) & 0x0C0C0C0Cu; x ^= t ^ (t << 2);
+    t = (x ^ (x >> 4)) & 0x00F000F0u; x ^= t ^ (t << 4);
+    t = (x ^ (x >> 8)) & 0x0000FF00u; x ^= t ^ (t << 8);
+    return x;
+}
+
 // Class 1 without dynamic programming: the pigeonhole filter.  A full-length candidate ending at a column j <= limit
 // is an occurrence of the whole adapter with at most kmax = thr[m] edits (substitutions, insertions, deletions) inside
 // read[0..limit).  Cut the adapter into kmax + 1 disjoint pieces: kmax edits touch at most kmax of them, so at least
 // one piece occurs EXACTLY in read[0..limit).  No piece occurrence there -> no candidate -> E wins.  (The converse does
 // not hold: a hit only sends the read to the general search.)  Piece occurrences are found for all positions at once:
-// per base x a mask of the positions holding x (2-bit words, even bits), then for a piece P
-//     R_len = all positions,   R_u = mask[P[u]] & (R_{u+1} >> one base)        (R_0 = start positions of P)
-// N is packed as A and may only add hits.  bm: this thread's scratch, 4 masks of W words, element (x * W + w) * stride
-// (shared memory on the device: the mask is selected by the adapter base, a run-time index).
+// the 2-bit words are split into a low-bit and a high-bit plane (one bit per position), giving per base x a mask of the
+// positions holding x; then for a piece P
+//     R_len = all positions,   R_u = mask[P[u]] & (R_{u+1} >> 1)        (R_0 = start positions of P)
+// N is packed as A and may only add hits.  bm: this thread's scratch, 4 masks of W / 2 words, element
+// (x * W / 2 + w) * stride (shared memory on the device: the mask is selected by the adapter base, a run-time index).
 template <int W>
 __host__ __device__ __forceinline__ bool k1_piece_hit(const PSeq<W> &p, int limit, int m, int kmax, u64 aw, u64 *bm, int stride)
 {
-    const u64 M5 = 0x5555555555555555ull;
+    constexpr int NP = W / 2;                                  // 64-position plane words
 #pragma unroll
-    for (int w = 0; w < W; w++) {
-        const u64 L = p.s[w] & M5, H = (p.s[w] >> 1) & M5;
-        bm[(0 * W + w) * stride] = M5 & ~(L | H);
-        bm[(1 * W + w) * stride] = L & ~H;
-        bm[(2 * W + w) * stride] = H & ~L;
-        bm[(3 * W + w) * stride] = L & H;
+    for (int w = 0; w < NP; w++) {
+        const u32 d0 = deinterleave32((u32)p.s[2 * w]), d1 = deinterleave32((u32)(p.s[2 * w] >> 32));
+        const u32 d2 = deinterleave32((u32)p.s[2 * w + 1]), d3 = deinterleave32((u32)(p.s[2 * w + 1] >> 32));
+        const u64 L = (u64)((d0 & 0xFFFFu) | (d1 << 16)) | ((u64)((d2 & 0xFFFFu) | (d3 << 16)) << 32);
+        const u64 H = (u64)((d0 >> 16) | (d1 & 0xFFFF0000u)) | ((u64)((d2 >> 16) | (d3 & 0xFFFF0000u)) << 32);
+        bm[(0 * NP + w) * stride] = ~(L | H);
+        bm[(1 * NP + w) * stride] = L & ~H;
+        bm[(2 * NP + w) * stride] = H & ~L;
+        bm[(3 * NP + w) * stride] = L & H;
     }
     const int np = kmax + 1;
     bool hit = false;
@@ -184,25 +199,25 @@ __host__ __device__ __forceinline__ bool k1_piece_hit(const PSeq<W> &p, int limi
         const int b0 = (q * m) / np, b1 = ((q + 1) * m) / np, len = b1 - b0;
         const int cnt = limit - len + 1;                       // start positions 0 .. limit - len
         if (cnt <= 0) continue;
-        u64 acc[W];
+        u64 acc[NP];
         {
             const int c = (int)((aw >> (2 * (b1 - 1))) & 3ull);
 #pragma unroll
-            for (int w = 0; w < W; w++) acc[w] = bm[(c * W + w) * stride];
+            for (int w = 0; w < NP; w++) acc[w] = bm[(c * NP + w) * stride];
         }
         for (int t = b1 - 2; t >= b0; t--) {
             const int c = (int)((aw >> (2 * t)) & 3ull);
 #pragma unroll
-            for (int w = 0; w < W; w++) {
-                const u64 up = (w + 1 < W) ? acc[w + 1] << 62 : 0ull;
-                acc[w] = bm[(c * W + w) * stride] & ((acc[w] >> 2) | up);
+            for (int w = 0; w < NP; w++) {
+                const u64 up = (w + 1 < NP) ? acc[w + 1] << 63 : 0ull;
+                acc[w] = bm[(c * NP + w) * stride] & ((acc[w] >> 1) | up);
             }
         }
         u64 any = 0;
 #pragma unroll
-        for (int w = 0; w < W; w++) {
-            const int lo = 32 * w;
-            u64 pm = (cnt <= lo) ? 0ull : (cnt >= lo + 32) ? M5 : (M5 & ((1ull << (2 * (cnt - lo))) - 1ull));
+        for (int w = 0; w < NP; w++) {
+            const int lo = 64 * w;
+            const u64 pm = (cnt <= lo) ? 0ull : (cnt >= lo + 64) ? ~0ull : ((1ull << (cnt - lo)) - 1ull);
             any |= acc[w] & pm;
         }
         hit = hit || any != 0ull;

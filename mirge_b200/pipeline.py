@@ -124,6 +124,74 @@ def iter_fastq_chunks_shard(path, rank, world, chunk_bytes=CHUNK_BYTES):
             yield carry
 
 
+def record_aligned_ranges(path, lo, hi, chunk_bytes=CHUNK_BYTES):
+    """[(a, b)] byte ranges of an uncompressed FASTQ file covering [lo, hi) in whole records, about chunk_bytes each."""
+    size = os.path.getsize(path)
+    out = []
+    with open(path, 'rb') as f:
+        a = lo
+        while a < hi:
+            b = hi if a + chunk_bytes >= hi else min(hi, find_record_start(f, a + chunk_bytes, size))
+            if b <= a:
+                b = hi
+            out.append((a, b))
+            a = b
+    return out
+
+
+class PinnedChunkReader:
+    """Streams record-aligned byte ranges of an uncompressed FASTQ file through two pinned staging buffers: a small
+    thread pool preads the next range (the GIL is released inside the system call) while the GPU works on the current
+    one, so the copies to the device are true asynchronous DMA instead of staged pageable copies."""
+
+    def __init__(self, path, ranges, threads=8):
+        import concurrent.futures
+        self.path, self.ranges, self.threads = path, ranges, max(1, threads)
+        cap = max((b - a for a, b in ranges), default=0) + 64
+        self.bufs = [self._alloc(cap), self._alloc(cap)]
+        self.pool = concurrent.futures.ThreadPoolExecutor(self.threads)
+        self.fd = os.open(path, os.O_RDONLY)
+
+    @staticmethod
+    def _alloc(n):
+        try:
+            import torch
+            t = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            return (t, t.numpy())            # the tensor owns the pinned allocation
+        except Exception:
+            return (None, np.empty(n, np.uint8))
+
+    def _fill(self, k):
+        a, b = self.ranges[k]
+        view = memoryview(self.bufs[k % 2][1])[:b - a]
+        step = -(-(b - a) // self.threads)
+        step = (step + 4095) & ~4095
+
+        def part(x):
+            got = x
+            end = min(b - a, x + step)
+            while got < end:
+                n = os.preadv(self.fd, [view[got:end]], a + got)
+                if n <= 0:
+                    raise IOError('short read on %s' % self.path)
+                got += n
+        futs = [self.pool.submit(part, x) for x in range(0, b - a, step)]
+        return futs
+
+    def __iter__(self):
+        pending = self._fill(0) if self.ranges else []
+        for k in range(len(self.ranges)):
+            for f in pending:
+                f.result()
+            a, b = self.ranges[k]
+            pending = self._fill(k + 1) if k + 1 < len(self.ranges) else []
+            yield self.bufs[k % 2][1][:b - a]       # the consumer must be done with it before the next-but-one range is read
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        os.close(self.fd)
+
+
 def peek_max_read_len(paths, n_records=2000):
     mx = 0
     for p in paths:
@@ -191,11 +259,27 @@ class AnnotateRun:
             opener = gzip.open if infile.endswith('.gz') else open
             with opener(infile, 'rb') as f:
                 phred = Engine.detect_phred(f.read(1 << 16))
-        for chunk in iter_fastq_chunks_shard(infile, self.rank, self.world):
-            if phred is None:
-                phred = Engine.detect_phred(chunk)        # decided by read #0, trim_file.py:104-109
-            self.engine.feed_fastq(sample_index, chunk, phred)
-            self.engine.sync()
+        if not infile.endswith('.gz'):
+            # plain text: this rank's byte range, cut at record boundaries, streamed through pinned double buffers
+            size = os.path.getsize(infile)
+            with open(infile, 'rb') as f:
+                lo = find_record_start(f, size * self.rank // self.world, size) if self.world > 1 else 0
+                hi = find_record_start(f, size * (self.rank + 1) // self.world, size) if self.world > 1 else size
+            reader = PinnedChunkReader(infile, record_aligned_ranges(infile, lo, hi))
+            try:
+                for chunk in reader:
+                    if phred is None:
+                        phred = Engine.detect_phred(chunk)    # decided by read #0, trim_file.py:104-109
+                    self.engine.feed_fastq(sample_index, chunk, phred)
+                    self.engine.sync()                        # the next range is already being read in the background
+            finally:
+                reader.close()
+        else:
+            for chunk in iter_fastq_chunks_shard(infile, self.rank, self.world):
+                if phred is None:
+                    phred = Engine.detect_phred(chunk)        # decided by read #0, trim_file.py:104-109
+                self.engine.feed_fastq(sample_index, chunk, phred)
+                self.engine.sync()
         p, k, _ = self.engine.stats()
         return (phred or 33), int(p[sample_index]), int(k[sample_index])
 

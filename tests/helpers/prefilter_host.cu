@@ -176,7 +176,7 @@ static void decide_one(const K1Pre &pre, const TrimParams &tp, const signed char
     if (cls == 0) { general = false; path = 0; }
     else if (cls == 1) {
         const bool scan = k1_full_candidate_scan<W>(p, lim, m, thr[m], peq8);
-        u64 bm[4 * W];
+        u64 bm[4 * (W / 2)];
         const bool piece = k1_piece_hit<W>(p, lim, m, thr[m], tp.aw[0][0], bm, 1);
         if (scan && !piece) { out[0] = -1000; out[1] = 9; return; }     // the filter must never miss a candidate
         general = (use_1b & 2) ? piece : scan;                           // bit 1: what the kernel does (pigeonhole filter)

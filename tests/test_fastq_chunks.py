@@ -50,3 +50,17 @@ def test_rank_shards_cover_the_file_once(tmp_path):
                     assert c.startswith(b'@r') and c.count(b'\n') % 4 == 0
                     seen += c.decode().split('\n')[0::4][:-1] if c.endswith(b'\n') else c.decode().split('\n')[0::4]
             assert sorted(seen) == sorted(r.split('\n')[0] for r in recs), (path, world)
+
+
+def test_pinned_reader_streams_whole_records(tmp_path):
+    from mirge_b200.pipeline import PinnedChunkReader, record_aligned_ranges
+    text = ''.join('@r%d\n%s\n+\n%s\n' % (i, 'ACGT' * (4 + i % 7), '@III' * (4 + i % 7)) for i in range(20000))
+    p = tmp_path / 'r.fastq'
+    p.write_text(text)
+    for cb in (5000, 100000, 1 << 30):
+        ranges = record_aligned_ranges(str(p), 0, len(text), cb)
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(text) and all(text[a] == '@' for a, _ in ranges)
+        r = PinnedChunkReader(str(p), ranges, threads=3)
+        got = b''.join(bytes(c) for c in r)
+        r.close()
+        assert got.decode() == text
