@@ -52,6 +52,7 @@ struct K0Params {
     int phred_base;     // 33 | 64
     int qual_cutoff;    // QualityTrimmer(0, cutoff, base), trim_file.py:30
     int max_len;        // 32 * W
+    int min_len;        // reads shorter than this are counted but not emitted (the length filter would drop them anyway)
 };
 
 // Carried from launch to launch (the regions of one chunk); lines[] alternates so that a launch
@@ -272,33 +273,37 @@ struct K0Stage {
 };
 #define K0_SL_DONE 0xFFu
 
-// 4. the records whose terminating newline has ordinal o in [pass_lo, pass_lo + K0_CAP - 4) and o = o0 (mod 4);
-// the record with ordinal o goes to slot slot0 + (o - o0) / 4.  Three phases:
-//   A  one thread per record: format checks, lengths, quality_trim_index -> meta, (a1, sl) for phase B
+// 4. the records whose terminating newline has ordinal o in [pass_lo, pass_lo + K0_CAP - 4) and o = o0 (mod 4).
+// Records are emitted in no particular order (K1 does not care): the pass takes its output slots with one atomic.
+// A read shorter than min_len can never survive the length filter (trimming only shortens), so it is checked and
+// counted but not emitted -- which also bounds the records of a region by bytes / (6 + 2 * min_len).  Three phases:
+//   A  one thread per record: format checks, lengths, quality_trim_index -> meta, (a1, sl) for phase B; a block scan
+//      of the emit flags compacts the pass
 //   B  one thread per 8 bases: two aligned-word groups -> 16 bits of bases + 8 N flags, stored in place in the stage
 //      (short critical path, nearly all lanes busy -- a thread per record leaves half of them idle for 13 steps)
 //   C  the stage goes out as three flat, coalesced copies
 template <int W>
 __device__ __forceinline__ void k0_pack_pass(const unsigned char *__restrict__ text, u64 reg_end, i64 delta, const unsigned char *buf,
-                                             const u16 *lst, u32 pass_lo, u32 o0, u32 T, u64 slot0, u64 rec_cap, const K0Params &prm,
-                                             K0Stage<W> &st, u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta,
-                                             u32 *err_word)
+                                             const u16 *lst, u32 pass_lo, u32 o0, u32 T, u64 *slot_counter, u64 rec_cap, const K0Params &prm,
+                                             K0Stage<W> &st, u32 *sh_scan, u64 *sh_slot, u64 *__restrict__ bases, u64 *__restrict__ nmask,
+                                             u32 *__restrict__ meta, u32 *err_word)
 {
     constexpr int NW = W / 2;
     const unsigned tid = threadIdx.x;
     const u32 lo = pass_lo > o0 ? pass_lo + ((o0 + 4 - (pass_lo & 3)) & 3) : o0;
     u32 hi = pass_lo + K0_CAP - 4;
     if (hi > T) hi = T;
-    const u32 nrec = hi > lo ? (hi - lo + 3) >> 2 : 0u;        // <= K0_RPP
-    if (nrec == 0) return;                                     // block-uniform
-    const u64 slotp = slot0 + ((lo - o0) >> 2);
+    const u32 nrec_all = hi > lo ? (hi - lo + 3) >> 2 : 0u;    // <= K0_RPP
+    if (nrec_all == 0) return;                                 // block-uniform
     // ---- A
-    if (tid < nrec) {
+    u32 emit = 0, mt = 0, a1s = 0, sls = 0;
+    u64 sq[W], nq[W / 2];
+    if (tid < nrec_all) {
         const u32 li = lo + 4 * tid + 4 - pass_lo;
         u32 l[5];
 #pragma unroll
         for (int k = 0; k < 5; k++) l[k] = lst[li - 4 + k];
-        u32 bad = 0, mt = 0;
+        u32 bad = 0;
         if (l[0] != K0_NONE) {
             const u32 a0 = l[0], a1 = l[1], a2 = l[2], a3 = l[3], a4 = l[4];
             if (buf[a0] != '@' || buf[a2] != '+') bad |= ERRF_FORMAT;       // cutadapt FormatError
@@ -326,8 +331,8 @@ __device__ __forceinline__ void k0_pack_pass(const unsigned char *__restrict__ t
                 if (start >= stop) { start = 0; stop = 0; }
             }
             mt = (u32)sl | ((u32)start << 8) | ((u32)stop << 16);
-            st.a1[tid] = (u16)a1;
-            st.sl[tid] = (u8)sl;
+            a1s = a1; sls = (u32)sl;
+            emit = sl >= prm.min_len ? 1u : 0u;
         } else {
             // a line of this record starts before the halo: find the missing starts in global memory, pack byte-wise
             u64 g[5];
@@ -343,7 +348,6 @@ __device__ __forceinline__ void k0_pack_pass(const unsigned char *__restrict__ t
             const u64 lim = reg_end;
             auto ld8 = [tb, gb, lim](u32 off) { return gb + off < lim ? (u32)tb[off] : 0u; };
             auto ld32 = [ld8](u32 off) { return ld8(off) | (ld8(off + 1) << 8) | (ld8(off + 2) << 16) | (ld8(off + 3) << 24); };
-            u64 sq[W], nq[NW];
 #pragma unroll
             for (int w = 0; w < W; w++) sq[w] = 0;
 #pragma unroll
@@ -351,17 +355,28 @@ __device__ __forceinline__ void k0_pack_pass(const unsigned char *__restrict__ t
             if (g[4] - gb >= 0xFFFFFF00ull) bad = ERRF_FORMAT;
             else k0_pack_record<W>(ld32, ld8, (u32)(g[0] - gb), (u32)(g[1] - gb), (u32)(g[2] - gb), (u32)(g[3] - gb), (u32)(g[4] - gb),
                                    prm, sq, nq, mt, bad);
-#pragma unroll
-            for (int w = 0; w < W; w++) st.bases[tid * W + w] = sq[w];
-#pragma unroll
-            for (int w = 0; w < NW; w++) st.nmask[tid * NW + w] = nq[w];
-            st.a1[tid] = 0;
-            st.sl[tid] = (u8)K0_SL_DONE;
+            sls = K0_SL_DONE;
+            emit = (int)(mt & 0xFFu) >= prm.min_len ? 1u : 0u;
         }
-        st.meta[tid] = mt;
         if (bad) atomicOr(err_word, bad);
     }
+    u32 nrec;
+    const u32 e = block_excl_scan(emit, sh_scan, &nrec);       // compacted index of this thread's record
+    if (emit) {
+        st.meta[e] = mt;
+        st.a1[e] = (u16)a1s;
+        st.sl[e] = (u8)sls;
+        if (sls == K0_SL_DONE) {
+#pragma unroll
+            for (int w = 0; w < W; w++) st.bases[e * W + w] = sq[w];
+#pragma unroll
+            for (int w = 0; w < NW; w++) st.nmask[e * NW + w] = nq[w];
+        }
+    }
+    if (tid == 0) *sh_slot = nrec ? atomicAdd(slot_counter, (u64)nrec) : 0ull;
     __syncthreads();
+    const u64 slotp = *sh_slot;
+    if (nrec == 0) return;                                     // block-uniform
     // ---- B
     {
         u16 *sb = reinterpret_cast<u16 *>(st.bases);
@@ -448,7 +463,6 @@ k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
         u32 T;
         const u32 ex = block_excl_scan(cnt, sh_scan, &T);
         u32 o0 = K0_CLAIM_NONE;
-        u64 slot0 = 0;
         for (u32 pass_lo = 0; pass_lo == 0 || pass_lo < T; pass_lo += K0_CAP - 4) {
             k0_fill_list(pass_lo, ex, mw, tile_start, m16, lst);
             __syncthreads();
@@ -459,17 +473,16 @@ k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
                     u32 claim = okm ? (u32)(__ffs(okm) - 1) : K0_CLAIM_NONE;
                     if (unk && (!okm || (u32)(__ffs(unk) - 1) < claim)) claim = K0_CLAIM_UNDECIDED;
                     if (tid == 0) {
-                        const u32 nrec = (claim < 4 && T > claim) ? (T - claim + 3) / 4 : 0u;
                         sh_claim = claim;
-                        sh_slot0 = nrec ? atomicAdd(&state->nrec, (u64)nrec) : 0ull;
                         info[tile] = T | (claim << 20);
                     }
                 }
                 __syncthreads();
-                o0 = sh_claim; slot0 = sh_slot0;
+                o0 = sh_claim;
             }
             if (o0 < 4)
-                k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, slot0, rec_cap, prm, stage, bases, nmask, meta, &state->err_spec);
+                k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, &state->nrec, rec_cap, prm, stage, sh_scan, &sh_slot0,
+                                bases, nmask, meta, &state->err_spec);
             __syncthreads();
         }
     }
@@ -505,13 +518,13 @@ k0_verify(const u32 *__restrict__ info, u32 ntiles, K0State *__restrict__ state,
     }
     bad = __syncthreads_or(bad);
     if (threadIdx.x == 0) {
-        if (bad) { state->need_exact = 1u; atomicAdd(n_exact, 1ull); }
+        if (bad) { state->need_exact = 1u; state->nrec = 0; atomicAdd(n_exact, 1ull); }     // the exact kernel emits again
         else {
             const u64 lines_out = lines_in + carry;
             state->need_exact = 0u;
             state->lines[par ^ 1] = lines_out;
             if (state->err_spec) atomicOr(err_flags, state->err_spec);
-            atomicAdd(processed, state->nrec);
+            atomicAdd(processed, (lines_out >> 2) - (lines_in >> 2));      // every record counts, emitted or not
             if (last_region && (lines_out & 3ull)) atomicOr(err_flags, ERRF_PARTIAL);
         }
     }
@@ -519,7 +532,6 @@ k0_verify(const u32 *__restrict__ info, u32 ntiles, K0State *__restrict__ state,
 
 // The exact path (runs only when k0_verify asks for it).  ctl[0] = tile ticket, ctl[1 + t] = status of
 // tile t (zeroed before the launch).  par: which K0State::lines slot holds the count carried in.
-// Record r of the chunk (lines 4r..4r+3) goes to slot r - (lines_in >> 2) of the output arrays.
 // last_region: the chunk ends with this launch, so the line count must be a multiple of four.
 template <int W>
 __global__ void __launch_bounds__(K0_THREADS)
@@ -534,6 +546,7 @@ k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
     __shared__ u32 sh_scan[33];
     __shared__ u32 sh_tile;
     __shared__ u64 sh_excl;
+    __shared__ u64 sh_slot0;
     __shared__ K0Stage<W> stage;
     if (!always && !state->need_exact) return;
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -590,15 +603,14 @@ k0_parse_pack(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end
             __syncthreads();
             const u64 G = sh_excl;
             const u32 o0 = (u32)((3ull - (G & 3ull)) & 3ull);        // first record-terminating newline of the tile
-            k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, ((G + o0) >> 2) - rec0, rec_cap, prm, stage, bases, nmask, meta, err_flags);
+            k0_pack_pass<W>(text, reg_end, halo_start, buf, lst, pass_lo, o0, T, &state->nrec, rec_cap, prm, stage, sh_scan, &sh_slot0,
+                            bases, nmask, meta, err_flags);
             __syncthreads();
         }
         if (tile == ntiles - 1 && tid == 0) {                // hand the line count on to the next launch
             const u64 lines_out = sh_excl + T;
             state->lines[par ^ 1] = lines_out;
-            const u64 nrec = (lines_out >> 2) - rec0;
-            state->nrec = nrec;
-            atomicAdd(processed, nrec);
+            atomicAdd(processed, (lines_out >> 2) - rec0);        // every record counts, emitted or not
             if (last_region && (lines_out & 3ull)) atomicOr(err_flags, ERRF_PARTIAL);
         }
         __syncthreads();

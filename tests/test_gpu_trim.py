@@ -145,7 +145,7 @@ def test_prefilter_classes_match_literal_dp(oracle_mod, adapter, maxlen):
     got = {s.decode(): int(c[0]) for s, c in zip(ee['seq'], ee['counts'])}
     assert got == want
     slow, c1, c2, _ = e.trim_classes()
-    assert c1 + c2 < len(reads)          # some reads are settled by exact comparisons alone
+    assert c2 < len(reads)               # some reads are settled by exact comparisons alone (c2 includes the class-1 reads the piece filter passes on)
     if adapter == ILLUMINA:
         assert c1 > 0
 
