@@ -759,15 +759,21 @@ k1_upsert(K1Buckets B, TableView<W> T, int sample, int flags)
     const unsigned lane = threadIdx.x & 31;
     const u64 warp0 = ((u64)blockIdx.x * K1U_THREADS + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * K1U_THREADS) >> 5;
     for (int b = 0; b < K1_NBUCKET; b++) {
-        for (u64 c = warp0; c < n_chunks; c += nwarps) {
-            if (B.chunk_bucket[c] != (u8)b) continue;                 // warp-uniform
-            PSeq<W> p;
-            int n = 0;
-            const bool on = k1q_load<W>(pool, c * K1B_CHUNK + lane, ~0ull, p, n);
-            bool lead; u32 id, cnt;
-            table_find_warp<W>(T, p, n, on, on ? pseq_hash<W>(p, n) : 0ull, lead, id, cnt);
-            if (flags & 0x800) { if (lead) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt); }     // diagnostic: count cache off
-            else count_cached<W>(cid, ccnt, T, sample, lead, id, cnt);
+        // a warp looks at 32 chunk labels with one coalesced load and works through the ones of bucket b
+        for (u64 c0 = warp0 * 32; c0 < n_chunks; c0 += nwarps * 32) {
+            const u8 cb = (c0 + lane < n_chunks) ? B.chunk_bucket[c0 + lane] : (u8)0xFF;
+            unsigned m = __ballot_sync(0xffffffffu, cb == (u8)b);
+            while (m) {
+                const u64 c = c0 + (u64)(__ffs(m) - 1);
+                m &= m - 1;
+                PSeq<W> p;
+                int n = 0;
+                const bool on = k1q_load<W>(pool, c * K1B_CHUNK + lane, ~0ull, p, n);
+                bool lead; u32 id, cnt;
+                table_find_warp<W>(T, p, n, on, on ? pseq_hash<W>(p, n) : 0ull, lead, id, cnt);
+                if (flags & 0x800) { if (lead) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt); }     // diagnostic: count cache off
+                else count_cached<W>(cid, ccnt, T, sample, lead, id, cnt);
+            }
         }
     }
     count_cache_flush<W>(cid, ccnt, T, sample);
