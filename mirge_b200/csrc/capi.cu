@@ -465,7 +465,7 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
         // bucket pool of the windowed upsert: every kept read once, plus the open chunks of every warp of three kernels
         cudaFree(ctx->d_bpool); cudaFree(ctx->d_bchunk);
         ctx->d_bpool = nullptr; ctx->d_bchunk = nullptr;
-        ctx->bpool_chunks = cap / K1B_CHUNK + (u64)3 * K1_NBUCKET * ctx->max_warps + 64;
+        ctx->bpool_chunks = cap / K1B_CHUNK + (u64)3 * K1_NBUCKET * ctx->max_warps / 2 + 64;   // + open chunks per CTA of three kernels, + a few handed back
         CK(cudaMalloc(&ctx->d_bpool, ctx->bpool_chunks * K1B_CHUNK * sizeof(K1QRec<W>)));
         CK(cudaMalloc(&ctx->d_bchunk, ctx->bpool_chunks));
         ctx->rec_cap = cap;

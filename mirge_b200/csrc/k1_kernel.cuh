@@ -490,7 +490,8 @@ __device__ __forceinline__ bool k1q_load(const K1QRec<W> *q, u64 i, u64 fill, PS
 // bits that choose its home slot, so a bucket's keys live in one contiguous 1/32 window of the table.  k1_upsert then
 // works through the buckets in order; while the grid is inside one bucket, the window it probes (32 MB) stays in L2.
 // Buckets are chains of 32-record chunks taken from one pool (any skew is fine -- all reads may be the same sequence);
-// chunk_bucket[c] names the bucket of chunk c, and a chunk is exactly one warp of work for k1_upsert.
+// chunk_bucket[c] names the bucket of chunk c, and a chunk is exactly one warp of work for k1_upsert.  The open
+// chunk of every bucket is shared by the CTA (shared-memory CAS), so few chunks are left partly filled.
 // ---------------------------------------------------------------------------
 #define K1_NBUCKET 32
 #define K1B_CHUNK 32
@@ -501,17 +502,17 @@ struct K1Buckets {
     u64 pool_chunks;
     u32 *err;
 };
-struct K1BState { u32 chunk[K1_NBUCKET]; u32 left[K1_NBUCKET]; };      // one per warp, shared memory
+struct K1BState { u64 cur[K1_NBUCKET]; };      // one per CTA, shared memory: open chunk << 32 | records in it (K1B_CHUNK: none open)
 
 __device__ __forceinline__ void k1b_init(K1BState *st)
 {
-    for (int b = threadIdx.x & 31; b < K1_NBUCKET; b += 32) { st->chunk[b] = 0; st->left[b] = 0; }
-    __syncwarp();
+    for (int b = threadIdx.x; b < K1_NBUCKET; b += blockDim.x) st->cur[b] = (u64)K1B_CHUNK;
+    __syncthreads();
 }
 
 // Every lane of a converged warp calls it; lanes with `push` hold a settled read of n bases with hash h.  Lanes bound
-// for the same bucket are grouped with one __match_any_sync; the group leaders update their buckets' chunk state
-// side by side (a new chunk costs one atomic on the pool counter).
+// for the same bucket are grouped with one __match_any_sync; the group leaders append to their buckets' open chunks
+// (state shared by the CTA, updated with a shared-memory CAS); a full chunk is replaced by a fresh one from the pool.
 template <int W>
 __device__ __forceinline__ void k1b_push(bool push, u64 h, const PSeq<W> &p, int n, const K1Buckets &B, K1BState *st)
 {
@@ -523,16 +524,29 @@ __device__ __forceinline__ void k1b_push(bool push, u64 h, const PSeq<W> &p, int
     u64 base0 = 0, base1 = 0;
     u32 nold = 0;
     if (push && (int)lane == leader) {
-        const u32 chunk = st->chunk[b], left = st->left[b];
-        base0 = (u64)chunk * K1B_CHUNK + (K1B_CHUNK - left);
-        if (c <= left) { nold = c; st->left[b] = left - c; }
-        else {
-            nold = left;
-            u64 nc = atomicAdd(B.n_chunks, 1ull);
-            if (nc >= B.pool_chunks) { atomicOr(B.err, ERRF_FULL); nc = 0; }
-            B.chunk_bucket[nc] = (u8)b;
-            st->chunk[b] = (u32)nc; st->left[b] = K1B_CHUNK - (c - left);
-            base1 = nc * K1B_CHUNK;
+        u64 fresh = ~0ull;                                              // a chunk taken from the pool, not yet installed
+        for (;;) {
+            const u64 old = *(volatile u64 *)&st->cur[b];
+            const u32 fill = (u32)old, chunk = (u32)(old >> 32);
+            if (fill + c <= K1B_CHUNK) {
+                if (atomicCAS(&st->cur[b], old, old + c) != old) continue;
+                base0 = (u64)chunk * K1B_CHUNK + fill; nold = c;
+                break;
+            }
+            if (fresh == ~0ull) {
+                fresh = atomicAdd(B.n_chunks, 1ull);
+                if (fresh >= B.pool_chunks) { atomicOr(B.err, ERRF_FULL); fresh = 0; }
+                B.chunk_bucket[fresh] = (u8)b;
+            }
+            const u32 room = K1B_CHUNK - fill;                          // the open chunk takes the first `room` records
+            if (atomicCAS(&st->cur[b], old, (fresh << 32) | (u64)(c - room)) != old) continue;
+            base0 = (u64)chunk * K1B_CHUNK + fill; nold = room; base1 = fresh * K1B_CHUNK;
+            fresh = ~0ull;
+            break;
+        }
+        if (fresh != ~0ull) {                                           // lost the race after allocating: hand the chunk back empty
+            K1QRec<W> *pool = reinterpret_cast<K1QRec<W> *>(B.pool);
+            for (u32 x = 0; x < K1B_CHUNK; x++) pool[fresh * K1B_CHUNK + x].n = K1Q_NONE;
         }
     }
     base0 = __shfl_sync(0xffffffffu, base0, leader);
@@ -551,19 +565,18 @@ __device__ __forceinline__ void k1b_push(bool push, u64 h, const PSeq<W> &p, int
             d[3] = make_ulonglong2((u64)(u32)n, 0ull);
         }
     }
-    __syncwarp();
 }
 
-// pad the open chunks of this warp
+// pad the CTA's open chunks (call after a __syncthreads() that follows the last push)
 template <int W>
 __device__ __forceinline__ void k1b_close(const K1Buckets &B, const K1BState *st)
 {
-    __syncwarp();
     K1QRec<W> *pool = reinterpret_cast<K1QRec<W> *>(B.pool);
-    for (int b = threadIdx.x & 31; b < K1_NBUCKET; b += 32) {
-        const u32 left = st->left[b];
-        const u64 base = (u64)st->chunk[b] * K1B_CHUNK + (K1B_CHUNK - left);
-        for (u32 x = 0; x < left; x++) pool[base + x].n = K1Q_NONE;
+    for (int b = threadIdx.x; b < K1_NBUCKET; b += blockDim.x) {
+        const u64 cur = st->cur[b];
+        const u32 fill = (u32)cur;
+        const u64 base = (cur >> 32) * K1B_CHUNK;
+        for (u32 x = fill; x < K1B_CHUNK; x++) pool[base + x].n = K1Q_NONE;
     }
 }
 
@@ -627,12 +640,12 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
                  K1Buckets B, int S, K1Counters ctr, K1Queues Q, int force_slow)
 {
     __shared__ u32 sh_hist[K1_HIST(W)];
-    __shared__ K1BState sh_bst[K1A_THREADS / 32];
+    __shared__ K1BState sh_bst;
     __shared__ K1Pre pre;
     __shared__ u64 sh_bm[4 * (W / 2) * K1A_THREADS];     // base-position masks of the pigeonhole filter
     for (int b = threadIdx.x; b < K1_HIST(W); b += K1A_THREADS) sh_hist[b] = 0;
     u32 *wh = sh_hist;
-    K1BState *bst = sh_bst + threadIdx.x / 32;
+    K1BState *bst = &sh_bst;
     k1b_init(bst);
     for (int b = threadIdx.x; b < (int)(sizeof(K1Pre) / 4); b += K1A_THREADS)
         reinterpret_cast<u32 *>(&pre)[b] = reinterpret_cast<const u32 *>(&pre_param)[b];
@@ -677,6 +690,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
         my_kept += k1_settle_warp<W>(p, nf, cls == 0, min_length, B, bst, wh);
     }
     k1q_close<W>(q2, wq2); k1q_close<W>(q3, wq3);
+    __syncthreads();
     k1b_close<W>(B, bst);
     k1_teardown<W>(my_kept, my_c1, ctr.slow_reads ? ctr.slow_reads + 1 : nullptr, sh_hist, ctr, S, sample);
 }
@@ -689,10 +703,10 @@ k1_general_search(int sample, TrimParams tp_param, K1Thr thr_param, K1Buckets B,
     __shared__ u32 ringh[K1_RING * K1_THREADS];
     __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ K1Shared sh;
-    __shared__ K1BState sh_bst[K1_THREADS / 32];
+    __shared__ K1BState sh_bst;
     k1_setup<W>(sh, sh_hist, tp_param, thr_param);
     u32 *wh = sh_hist;
-    K1BState *bst = sh_bst + threadIdx.x / 32;
+    K1BState *bst = &sh_bst;
     k1b_init(bst);
     const u64 n2 = Q.n[0];
     const K1QRec<W> *q2 = reinterpret_cast<const K1QRec<W> *>(Q.q2);
@@ -709,6 +723,7 @@ k1_general_search(int sample, TrimParams tp_param, K1Thr thr_param, K1Buckets B,
         my_kept += k1_settle_warp<W>(ps, nfs, on && nfs != K1_SLOW, sh.tp.min_length, B, bst, wh);
     }
     k1q_close<W>(q3, wq3);
+    __syncthreads();
     k1b_close<W>(B, bst);
     k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 2 : nullptr, sh_hist, ctr, S, sample);
 }
@@ -719,10 +734,10 @@ k1_slow_search(int sample, TrimParams tp_param, K1Thr thr_param, K1Buckets B, in
 {
     __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ K1Shared sh;
-    __shared__ K1BState sh_bst[K1_THREADS / 32];
+    __shared__ K1BState sh_bst;
     k1_setup<W>(sh, sh_hist, tp_param, thr_param);
     u32 *wh = sh_hist;
-    K1BState *bst = sh_bst + threadIdx.x / 32;
+    K1BState *bst = &sh_bst;
     k1b_init(bst);
     const u64 n3 = Q.n[1];
     const K1QRec<W> *q3 = reinterpret_cast<const K1QRec<W> *>(Q.q3);
@@ -738,6 +753,7 @@ k1_slow_search(int sample, TrimParams tp_param, K1Thr thr_param, K1Buckets B, in
         __syncwarp();
         my_kept += k1_settle_warp<W>(ps, nfs, on, sh.tp.min_length, B, bst, wh);
     }
+    __syncthreads();
     k1b_close<W>(B, bst);
     k1_teardown<W>(my_kept, my_n, ctr.slow_reads, sh_hist, ctr, S, sample);
 }
