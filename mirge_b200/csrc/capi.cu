@@ -27,7 +27,7 @@ enum KernelId {
     KID_K0_PACK, KID_K1_TRIM, KID_K3_KEYS, KID_K3_SORT,
     KID_K3_BOUNDS, KID_K3_REDUCE, KID_K3_FINAL, KID_LIB_BUILD, KID_EXCHANGE, KID_H2D, KID_RESET, KID_GENOME, KID_IMPORT,
     KID_K2_ROUND0 = 16,   // .. KID_K2_ROUND0 + 9
-    KID_K1_CLASSIFY = 26, KID_K1_UPSERT, KID_K1_GENERAL, KID_K1_SLOW,
+    KID_K1_CLASSIFY = 26, KID_K1_SCAN, KID_K1_GENERAL, KID_K1_SLOW,
     KID_N = 30
 };
 static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
@@ -35,7 +35,7 @@ static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
     "k3_radix_sort", "k3_seg_bounds", "k3_seg_reduce", "k3_finalize", "lib_build", "exchange", "h2d_copy", "reset_memset", "k2g_genome_all_hits", "exchange_import",
     "k2_round0_mirna_exact", "k2_round1_hairpin", "k2_round2_mature_trna", "k2_round3_pre_trna", "k2_round4_snorna",
     "k2_round5_rrna", "k2_round6_ncrna_others", "k2_round7_mrna", "k2_round8_isomir", "k2_round9_spikein",
-    "k1a_classify_partition", "k1u_windowed_upsert", "k1c_general_search", "k1d_slow_search", "", ""};
+    "k1a_classify_collapse", "", "k1c_general_search", "k1d_slow_search", "", ""};
 
 struct DevLib {
     u64 *seq = nullptr, *amb = nullptr;
@@ -72,7 +72,6 @@ struct mirge_ctx {
     u32 *d_k0info = nullptr; size_t k0info_cap = 0; // speculative path: newline count | claim per tile
     K0State *d_k0state = nullptr;
     u64 *d_bases = nullptr, *d_nmask = nullptr; u32 *d_meta = nullptr; size_t rec_cap = 0;
-    void *d_bpool = nullptr; u8 *d_bchunk = nullptr; u64 bpool_chunks = 0;      // bucket pool of the windowed upsert
     void *d_q2 = nullptr, *d_q3 = nullptr; u64 *d_qn = nullptr, *d_part = nullptr;   // K1 class queues (records, rec_cap entries each), their fills; exchange partition counters
     // unique table
     void *d_slots = nullptr; u64 table_cap = 0;
@@ -317,7 +316,7 @@ void mirge_destroy(mirge_ctx *ctx)
     for (int i = 0; i < MIRGE_N_LIBS; i++) free_lib(ctx->libs[i]);
     cudaFree(ctx->d_text); cudaFree(ctx->d_k0ctl); cudaFree(ctx->d_k0info); cudaFree(ctx->d_k0state);
     cudaFree(ctx->d_bases); cudaFree(ctx->d_nmask); cudaFree(ctx->d_meta);
-    cudaFree(ctx->d_q2); cudaFree(ctx->d_q3); cudaFree(ctx->d_qn); cudaFree(ctx->d_part); cudaFree(ctx->d_bpool); cudaFree(ctx->d_bchunk);
+    cudaFree(ctx->d_q2); cudaFree(ctx->d_q3); cudaFree(ctx->d_qn); cudaFree(ctx->d_part);
     cudaFree(ctx->d_slots); cudaFree(ctx->d_useq); cudaFree(ctx->d_unmask); cudaFree(ctx->d_ulen); cudaFree(ctx->d_counts);
     cudaFree(ctx->d_round_of); cudaFree(ctx->d_mm_of); cudaFree(ctx->d_ref_of); cudaFree(ctx->d_pos_of);
     cudaFree(ctx->d_ctr); cudaFree(ctx->d_len_hist); cudaFree(ctx->d_todo[0]); cudaFree(ctx->d_todo[1]);
@@ -462,12 +461,6 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
         const size_t qcap = cap + (size_t)K1Q_CHUNK * 2 * ctx->max_warps;
         CK(cudaMalloc(&ctx->d_q2, qcap * sizeof(K1QRec<W>)));
         CK(cudaMalloc(&ctx->d_q3, qcap * sizeof(K1QRec<W>)));
-        // bucket pool of the windowed upsert: every kept read once, plus the open chunks of every warp of three kernels
-        cudaFree(ctx->d_bpool); cudaFree(ctx->d_bchunk);
-        ctx->d_bpool = nullptr; ctx->d_bchunk = nullptr;
-        ctx->bpool_chunks = cap / K1B_CHUNK + (u64)3 * K1_NBUCKET * ctx->max_warps / 2 + 64;   // + open chunks per CTA of three kernels, + a few handed back
-        CK(cudaMalloc(&ctx->d_bpool, ctx->bpool_chunks * K1B_CHUNK * sizeof(K1QRec<W>)));
-        CK(cudaMalloc(&ctx->d_bchunk, ctx->bpool_chunks));
         ctx->rec_cap = cap;
     }
     const u64 max_tiles = (max_region + 1 + K0_TILE - 1) / K0_TILE;
@@ -497,23 +490,19 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
               ctx->d_bases, ctx->d_nmask, ctx->d_meta, err_flags, processed, exact_only ? 1 : 0); }
         const u64 *nrec = &ctx->d_k0state->nrec;
         const u64 rec_bound = len / rec_min_bytes + 1;              // sizes the grids only
-        { ProfScope ps(ctx, KID_K1_TRIM, 4);
+        { ProfScope ps(ctx, KID_K1_TRIM, 3);
           K1Queues Q; Q.n = ctx->d_qn; Q.q2 = ctx->d_q2; Q.q3 = ctx->d_q3;
-          K1Buckets B; B.pool = ctx->d_bpool; B.chunk_bucket = ctx->d_bchunk; B.n_chunks = ctx->d_qn + 2; B.pool_chunks = ctx->bpool_chunks;
-          B.err = (u32 *)(ctx->d_ctr + 1);
           const TableView<W> T = table_view<W>(ctx);
-          CK(cudaMemsetAsync(ctx->d_qn, 0, 3 * sizeof(u64), st));
+          CK(cudaMemsetAsync(ctx->d_qn, 0, 2 * sizeof(u64), st));
           { ProfScope p1(ctx, KID_K1_CLASSIFY, 0);
             k1_trim_collapse<W><<<wave_grid(k1_trim_collapse<W>, K1A_THREADS, rec_bound), K1A_THREADS, 0, st>>>(
-                ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->pre, ctx->thr, B, ctx->S, kc, Q, ctx->force_slow); }
+                ctx->d_bases, ctx->d_nmask, ctx->d_meta, nrec, sample, ctx->tp, ctx->pre, ctx->thr, T, kc, Q, ctx->force_slow); }
           // the queue fills live on the device: fixed grids, grid-stride loops bounded by the fill
           { ProfScope p1(ctx, KID_K1_GENERAL, 0);
-            k1_general_search<W><<<wave_grid(k1_general_search<W>, K1_THREADS, rec_bound), K1_THREADS, 0, st>>>(sample, ctx->tp, ctx->thr, B, ctx->S, kc, Q); }
+            k1_general_search<W><<<wave_grid(k1_general_search<W>, K1_THREADS, rec_bound), K1_THREADS, 0, st>>>(sample, ctx->tp, ctx->thr, T, kc, Q); }
           { ProfScope p1(ctx, KID_K1_SLOW, 0);
-            k1_slow_search<W><<<wave_grid(k1_slow_search<W>, K1_THREADS, rec_bound), K1_THREADS, 0, st>>>(sample, ctx->tp, ctx->thr, B, ctx->S, kc, Q,
-                                                            (ctx->force_slow & 2) ? 1 : 0); }
-          { ProfScope p1(ctx, KID_K1_UPSERT, 0);
-            k1_upsert<W><<<wave_grid(k1_upsert<W>, K1U_THREADS, rec_bound * 2), K1U_THREADS, 0, st>>>(B, T, sample, ctx->force_slow); } }
+            k1_slow_search<W><<<wave_grid(k1_slow_search<W>, K1_THREADS, rec_bound), K1_THREADS, 0, st>>>(sample, ctx->tp, ctx->thr, T, kc, Q,
+                                                            (ctx->force_slow & 2) ? 1 : 0); } }
     }
     CK(cudaGetLastError());
     ctx->annotated = false; ctx->tallied = false;

@@ -483,114 +483,6 @@ __device__ __forceinline__ bool k1q_load(const K1QRec<W> *q, u64 i, u64 fill, PS
     return true;
 }
 
-// ---------------------------------------------------------------------------
-// Windowed upsert.  The unique table (1 GB at the bench size) is eight times the L2: upserting reads in arrival
-// order makes every probe a random DRAM access (this bound K1 in round 1).  Instead the kernels that settle a read
-// only PARTITION it: the read goes, as a 32-byte record, into the bucket named by the top bits of its hash -- the same
-// bits that choose its home slot, so a bucket's keys live in one contiguous 1/32 window of the table.  k1_upsert then
-// works through the buckets in order; while the grid is inside one bucket, the window it probes (32 MB) stays in L2.
-// Buckets are chains of 32-record chunks taken from one pool (any skew is fine -- all reads may be the same sequence);
-// chunk_bucket[c] names the bucket of chunk c, and a chunk is exactly one warp of work for k1_upsert.  The open
-// chunk of every bucket is shared by the CTA (shared-memory CAS), so few chunks are left partly filled.
-// ---------------------------------------------------------------------------
-#define K1_NBUCKET 32
-#define K1B_CHUNK 32
-struct K1Buckets {
-    void *pool;           // K1QRec<W>[pool_chunks * K1B_CHUNK]
-    u8 *chunk_bucket;     // [pool_chunks]
-    u64 *n_chunks;        // chunks handed out (device counter)
-    u64 pool_chunks;
-    u32 *err;
-};
-struct K1BState { u64 cur[K1_NBUCKET]; };      // one per CTA, shared memory: open chunk << 32 | records in it (K1B_CHUNK: none open)
-
-__device__ __forceinline__ void k1b_init(K1BState *st)
-{
-    for (int b = threadIdx.x; b < K1_NBUCKET; b += blockDim.x) st->cur[b] = (u64)K1B_CHUNK;
-    __syncthreads();
-}
-
-// Every lane of a converged warp calls it; lanes with `push` hold a settled read of n bases with hash h.  Lanes bound
-// for the same bucket are grouped with one __match_any_sync; the group leaders append to their buckets' open chunks
-// (state shared by the CTA, updated with a shared-memory CAS); a full chunk is replaced by a fresh one from the pool.
-template <int W>
-__device__ __forceinline__ void k1b_push(bool push, u64 h, const PSeq<W> &p, int n, const K1Buckets &B, K1BState *st)
-{
-    const unsigned lane = threadIdx.x & 31;
-    const u32 b = (u32)(h >> 59);                                       // top log2(K1_NBUCKET) bits
-    const unsigned peers = __match_any_sync(0xffffffffu, push ? b : (u32)(K1_NBUCKET + lane));
-    const int leader = __ffs(peers) - 1;
-    const u32 c = __popc(peers), rank = __popc(peers & ((1u << lane) - 1u));
-    u64 base0 = 0, base1 = 0;
-    u32 nold = 0;
-    if (push && (int)lane == leader) {
-        u64 fresh = ~0ull;                                              // a chunk taken from the pool, not yet installed
-        for (;;) {
-            const u64 old = *(volatile u64 *)&st->cur[b];
-            const u32 fill = (u32)old, chunk = (u32)(old >> 32);
-            if (fill + c <= K1B_CHUNK) {
-                if (atomicCAS(&st->cur[b], old, old + c) != old) continue;
-                base0 = (u64)chunk * K1B_CHUNK + fill; nold = c;
-                break;
-            }
-            if (fresh == ~0ull) {
-                fresh = atomicAdd(B.n_chunks, 1ull);
-                if (fresh >= B.pool_chunks) { atomicOr(B.err, ERRF_FULL); fresh = 0; }
-                B.chunk_bucket[fresh] = (u8)b;
-            }
-            const u32 room = K1B_CHUNK - fill;                          // the open chunk takes the first `room` records
-            if (atomicCAS(&st->cur[b], old, (fresh << 32) | (u64)(c - room)) != old) continue;
-            base0 = (u64)chunk * K1B_CHUNK + fill; nold = room; base1 = fresh * K1B_CHUNK;
-            fresh = ~0ull;
-            break;
-        }
-        if (fresh != ~0ull) {                                           // lost the race after allocating: hand the chunk back empty
-            K1QRec<W> *pool = reinterpret_cast<K1QRec<W> *>(B.pool);
-            for (u32 x = 0; x < K1B_CHUNK; x++) pool[fresh * K1B_CHUNK + x].n = K1Q_NONE;
-        }
-    }
-    base0 = __shfl_sync(0xffffffffu, base0, leader);
-    base1 = __shfl_sync(0xffffffffu, base1, leader);
-    nold = __shfl_sync(0xffffffffu, nold, leader);
-    if (push) {
-        const u64 slot = rank < nold ? base0 + rank : base1 + (rank - nold);
-        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(reinterpret_cast<K1QRec<W> *>(B.pool) + slot);
-        if (W == 2) {
-            d[0] = make_ulonglong2(p.s[0], p.s[1]);
-            d[1] = make_ulonglong2(p.nm[0], (u64)(u32)n);
-        } else {
-            d[0] = make_ulonglong2(p.s[0], p.s[1]);
-            d[1] = make_ulonglong2(p.s[W - 2], p.s[W - 1]);
-            d[2] = make_ulonglong2(p.nm[0], p.nm[W / 2 - 1]);
-            d[3] = make_ulonglong2((u64)(u32)n, 0ull);
-        }
-    }
-}
-
-// pad the CTA's open chunks (call after a __syncthreads() that follows the last push)
-template <int W>
-__device__ __forceinline__ void k1b_close(const K1Buckets &B, const K1BState *st)
-{
-    K1QRec<W> *pool = reinterpret_cast<K1QRec<W> *>(B.pool);
-    for (int b = threadIdx.x; b < K1_NBUCKET; b += blockDim.x) {
-        const u64 cur = st->cur[b];
-        const u32 fill = (u32)cur;
-        const u64 base = (cur >> 32) * K1B_CHUNK;
-        for (u32 x = fill; x < K1B_CHUNK; x++) pool[base + x].n = K1Q_NONE;
-    }
-}
-
-// Length filter + read-length histogram + partition for one converged warp: lanes with `on` hold a trimmed read.
-template <int W>
-__device__ __forceinline__ u32 k1_settle_warp(PSeq<W> &p, int n, bool on, int min_length, const K1Buckets &B, K1BState *st, u32 *wh)
-{
-    const bool keep = on && n >= min_length;
-    if (keep) pseq_truncate<W>(p, n);
-    k1b_push<W>(keep, keep ? pseq_hash<W>(p, n) : 0ull, p, n, B, st);
-    if (keep) atomicAdd(&wh[n], 1u);
-    return keep ? 1u : 0u;
-}
-
 struct K1Shared {
     TrimParams tp;                                  // dynamic indexing by adapter: keep it out of local memory
     signed char thr[MIRGE_MAX_ADAPTER_LEN + 1];
@@ -637,16 +529,16 @@ template <int W>
 __global__ void __launch_bounds__(K1A_THREADS)
 k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
                  const u64 *__restrict__ n_records_ptr, int sample, TrimParams tp_param, K1Pre pre_param, K1Thr thr_param,
-                 K1Buckets B, int S, K1Counters ctr, K1Queues Q, int force_slow)
+                 TableView<W> T, K1Counters ctr, K1Queues Q, int force_slow)
 {
     __shared__ u32 sh_hist[K1_HIST(W)];
-    __shared__ K1BState sh_bst;
+    __shared__ u32 sh_cid[K1_CC * (K1A_THREADS / 32)], sh_ccnt[K1_CC * (K1A_THREADS / 32)];
     __shared__ K1Pre pre;
     __shared__ u64 sh_bm[4 * (W / 2) * K1A_THREADS];     // base-position masks of the pigeonhole filter
     for (int b = threadIdx.x; b < K1_HIST(W); b += K1A_THREADS) sh_hist[b] = 0;
+    for (int b = threadIdx.x; b < K1_CC * (K1A_THREADS / 32); b += K1A_THREADS) { sh_cid[b] = 0xFFFFFFFFu; sh_ccnt[b] = 0; }
     u32 *wh = sh_hist;
-    K1BState *bst = &sh_bst;
-    k1b_init(bst);
+    u32 *cid = sh_cid + K1_CC * (threadIdx.x / 32), *ccnt = sh_ccnt + K1_CC * (threadIdx.x / 32);
     for (int b = threadIdx.x; b < (int)(sizeof(K1Pre) / 4); b += K1A_THREADS)
         reinterpret_cast<u32 *>(&pre)[b] = reinterpret_cast<const u32 *>(&pre_param)[b];
     __syncthreads();
@@ -686,28 +578,31 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
         }
         k1q_push<W>(cls == 2, Q.n + 0, q2, wq2, p, n);
         k1q_push<W>(cls == 3, Q.n + 1, q3, wq3, p, n);
-        if (force_slow & 0x200) { my_kept += (cls == 0 && nf >= min_length); continue; }     // diagnostic: classification only
-        my_kept += k1_settle_warp<W>(p, nf, cls == 0, min_length, B, bst, wh);
+        const bool keep = cls == 0 && nf >= min_length;
+        if (force_slow & 0x200) { my_kept += keep; continue; }             // diagnostic: classification only
+        if (keep) pseq_truncate<W>(p, nf);
+        bool lead; u32 id, cnt;
+        table_find_warp<W>(T, p, nf, keep, keep ? pseq_hash<W>(p, nf) : 0ull, lead, id, cnt);
+        if (force_slow & 0x100) { }                                        // diagnostic: no count updates
+        else if (force_slow & 0x800) { if (lead) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt); }   // count cache off
+        else count_cached<W>(cid, ccnt, T, sample, lead, id, cnt);
+        if (keep) { atomicAdd(&wh[nf], 1u); my_kept++; }
     }
+    count_cache_flush<W>(cid, ccnt, T, sample);
     k1q_close<W>(q2, wq2); k1q_close<W>(q3, wq3);
-    __syncthreads();
-    k1b_close<W>(B, bst);
-    k1_teardown<W>(my_kept, my_c1, ctr.slow_reads ? ctr.slow_reads + 1 : nullptr, sh_hist, ctr, S, sample);
+    k1_teardown<W>(my_kept, my_c1, ctr.slow_reads ? ctr.slow_reads + 1 : nullptr, sh_hist, ctr, T.S, sample);
 }
 
 template <int W>
 __global__ void __launch_bounds__(K1_THREADS)
-k1_general_search(int sample, TrimParams tp_param, K1Thr thr_param, K1Buckets B, int S, K1Counters ctr, K1Queues Q)
+k1_general_search(int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q)
 {
     __shared__ u64 ring[K1_RING * K1_THREADS];
     __shared__ u32 ringh[K1_RING * K1_THREADS];
     __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ K1Shared sh;
-    __shared__ K1BState sh_bst;
     k1_setup<W>(sh, sh_hist, tp_param, thr_param);
     u32 *wh = sh_hist;
-    K1BState *bst = &sh_bst;
-    k1b_init(bst);
     const u64 n2 = Q.n[0];
     const K1QRec<W> *q2 = reinterpret_cast<const K1QRec<W> *>(Q.q2);
     K1QRec<W> *q3 = reinterpret_cast<K1QRec<W> *>(Q.q3);
@@ -720,25 +615,20 @@ k1_general_search(int sample, TrimParams tp_param, K1Thr thr_param, K1Buckets B,
         my_n += on;
         const int nfs = k1_trim_fast<W>(ps, ns, sh.tp, sh.thr, ring + threadIdx.x, ringh + threadIdx.x, sh.peq8);   // warp-collective
         k1q_push<W>(on && nfs == K1_SLOW, Q.n + 1, q3, wq3, ps, ns);
-        my_kept += k1_settle_warp<W>(ps, nfs, on && nfs != K1_SLOW, sh.tp.min_length, B, bst, wh);
+        my_kept += k1_finish_warp<W>(ps, nfs, on && nfs != K1_SLOW, sh.tp.min_length, T, sample, wh);
     }
     k1q_close<W>(q3, wq3);
-    __syncthreads();
-    k1b_close<W>(B, bst);
-    k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 2 : nullptr, sh_hist, ctr, S, sample);
+    k1_teardown<W>(my_kept, my_n, ctr.slow_reads ? ctr.slow_reads + 2 : nullptr, sh_hist, ctr, T.S, sample);
 }
 
 template <int W>
 __global__ void __launch_bounds__(K1_THREADS)
-k1_slow_search(int sample, TrimParams tp_param, K1Thr thr_param, K1Buckets B, int S, K1Counters ctr, K1Queues Q, int literal)
+k1_slow_search(int sample, TrimParams tp_param, K1Thr thr_param, TableView<W> T, K1Counters ctr, K1Queues Q, int literal)
 {
     __shared__ u32 sh_hist[K1_HIST(W)];
     __shared__ K1Shared sh;
-    __shared__ K1BState sh_bst;
     k1_setup<W>(sh, sh_hist, tp_param, thr_param);
     u32 *wh = sh_hist;
-    K1BState *bst = &sh_bst;
-    k1b_init(bst);
     const u64 n3 = Q.n[1];
     const K1QRec<W> *q3 = reinterpret_cast<const K1QRec<W> *>(Q.q3);
     u32 my_kept = 0, my_n = 0;
@@ -751,46 +641,7 @@ k1_slow_search(int sample, TrimParams tp_param, K1Thr thr_param, K1Buckets B, in
             my_n++;
         }
         __syncwarp();
-        my_kept += k1_settle_warp<W>(ps, nfs, on, sh.tp.min_length, B, bst, wh);
+        my_kept += k1_finish_warp<W>(ps, nfs, on, sh.tp.min_length, T, sample, wh);
     }
-    __syncthreads();
-    k1b_close<W>(B, bst);
-    k1_teardown<W>(my_kept, my_n, ctr.slow_reads, sh_hist, ctr, S, sample);
-}
-
-// The collapse itself (quantReads.py:9-16): bucket by bucket, one warp per 32-record chunk; duplicates inside the chunk
-// are folded, hot sequences go through the per-warp count cache.
-#define K1U_THREADS 256
-template <int W>
-__global__ void __launch_bounds__(K1U_THREADS)
-k1_upsert(K1Buckets B, TableView<W> T, int sample, int flags)
-{
-    __shared__ u32 sh_cid[K1_CC * (K1U_THREADS / 32)], sh_ccnt[K1_CC * (K1U_THREADS / 32)];
-    for (int b = threadIdx.x; b < K1_CC * (K1U_THREADS / 32); b += K1U_THREADS) { sh_cid[b] = 0xFFFFFFFFu; sh_ccnt[b] = 0; }
-    __syncthreads();
-    u32 *cid = sh_cid + K1_CC * (threadIdx.x / 32), *ccnt = sh_ccnt + K1_CC * (threadIdx.x / 32);
-    u64 n_chunks = *B.n_chunks;
-    if (n_chunks > B.pool_chunks) n_chunks = B.pool_chunks;
-    const K1QRec<W> *pool = reinterpret_cast<const K1QRec<W> *>(B.pool);
-    const unsigned lane = threadIdx.x & 31;
-    const u64 warp0 = ((u64)blockIdx.x * K1U_THREADS + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * K1U_THREADS) >> 5;
-    for (int b = 0; b < K1_NBUCKET; b++) {
-        // a warp looks at 32 chunk labels with one coalesced load and works through the ones of bucket b
-        for (u64 c0 = warp0 * 32; c0 < n_chunks; c0 += nwarps * 32) {
-            const u8 cb = (c0 + lane < n_chunks) ? B.chunk_bucket[c0 + lane] : (u8)0xFF;
-            unsigned m = __ballot_sync(0xffffffffu, cb == (u8)b);
-            while (m) {
-                const u64 c = c0 + (u64)(__ffs(m) - 1);
-                m &= m - 1;
-                PSeq<W> p;
-                int n = 0;
-                const bool on = k1q_load<W>(pool, c * K1B_CHUNK + lane, ~0ull, p, n);
-                bool lead; u32 id, cnt;
-                table_find_warp<W>(T, p, n, on, on ? pseq_hash<W>(p, n) : 0ull, lead, id, cnt);
-                if (flags & 0x800) { if (lead) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt); }     // diagnostic: count cache off
-                else count_cached<W>(cid, ccnt, T, sample, lead, id, cnt);
-            }
-        }
-    }
-    count_cache_flush<W>(cid, ccnt, T, sample);
+    k1_teardown<W>(my_kept, my_n, ctr.slow_reads, sh_hist, ctr, T.S, sample);
 }
