@@ -23,6 +23,7 @@ struct LibView {
     const u32 *blk_ref;    // [total / 64 + 1] entry holding the first base of each 64-base block
     int n_refs;
     u32 total;
+    u32 max_ref_len;       // longest entry: a longer query has no placement
 };
 
 struct KmerTab {
