@@ -270,6 +270,8 @@ def run_ours(args):
         return e
 
     eng = make_engine(S)
+    if N == 1:
+        eng.annotate_while_feeding(True)     # end-to-end mode: the rounds of region r run under the copy of region r+1
     sample = rank
 
     def step(resident):

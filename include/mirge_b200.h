@@ -100,8 +100,10 @@ int mirge_get_stats(mirge_ctx *ctx, uint64_t *processed, uint64_t *kept, uint64_
 int mirge_load_library(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_ascii, const uint64_t *offsets);
 
 /* runAnnotationPipeline(...) (utils/runAnnotationPipeline.py:566,636-705): all
- * rounds in order over the still un-annotated unique sequences, including the
- * poly-T pre-tRNA round (:664-704). */
+ * rounds in order over the unique sequences that have not been looked at yet
+ * (incremental: sequences added by later feeds are picked up by the next call;
+ * loading a library or rebuilding the table starts over), including the poly-T
+ * pre-tRNA round (:664-704). */
 int mirge_annotate(mirge_ctx *ctx);
 
 /* -- genome passes --------------------------------------- */
@@ -125,6 +127,14 @@ int mirge_genome_pass(mirge_ctx *ctx, uint64_t n, const char *reads, int stride,
  * (row numbers of mirge_export_unique). */
 int mirge_genome_pass_ids(mirge_ctx *ctx, uint64_t n, const uint32_t *ids, int mode, int param, int seedlen, int trim3, int norc,
                           uint32_t *counts);
+
+/* Options.  MIRGE_OPT_ANNOTATE_WHILE_FEEDING (default off): mirge_feed_fastq runs the
+ * mapping rounds on the sequences each 64 MiB region added while the next region
+ * is being copied, so mirge_annotate only has the last region left -- the rounds
+ * hide behind the host-to-device copies.  Libraries must be loaded before
+ * feeding; leave it off when the table is rebuilt afterwards (multi-GPU exchange). */
+enum { MIRGE_OPT_ANNOTATE_WHILE_FEEDING = 1 };
+int mirge_set_option(mirge_ctx *ctx, int option, int value);
 
 /* -- stage 3: tallies ----------------------------------------------------- */
 

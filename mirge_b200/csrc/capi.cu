@@ -89,6 +89,8 @@ struct mirge_ctx {
     u64 *d_todo_n = nullptr;        // [MIRGE_N_ROUNDS + 1]
     u64 *d_round_stats = nullptr;   // [2][MIRGE_N_ROUNDS]
     bool annotated = false;
+    bool annotate_while_feeding = false;
+    u64 *d_annot = nullptr;         // [0] ids annotated so far, [1] base and [2] size of the range being annotated
     // tallies
     i64 *d_mir_quant = nullptr, *d_mir_iscan = nullptr, *d_lib_totals = nullptr;
     int tally_nmir = -1;
@@ -103,6 +105,8 @@ struct mirge_ctx {
 };
 
 static thread_local std::string g_create_err;
+static int annot_clear(mirge_ctx *ctx);
+template <int W> static int annotate_impl(mirge_ctx *ctx);
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -290,12 +294,13 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_k0state, sizeof(K0State)));
     CK(cudaMalloc(&ctx->d_qn, 4 * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_round_stats, 2 * MIRGE_N_ROUNDS * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_annot, 4 * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_lib_totals, (size_t)n_samples * MIRGE_N_TOTALS * sizeof(i64)));
     CK(cudaMemsetAsync(ctx->d_slots, 0, cap * esz, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counts, 0, max_unique * (size_t)n_samples * sizeof(u32), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_ctr, 0, (6 + 2 * (size_t)n_samples) * sizeof(u64), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_len_hist, 0, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), ctx->stream));
+    { int rc = annot_clear(ctx); if (rc) return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
     return MIRGE_OK;
 }
@@ -321,7 +326,7 @@ void mirge_destroy(mirge_ctx *ctx)
     cudaFree(ctx->d_slots); cudaFree(ctx->d_useq); cudaFree(ctx->d_unmask); cudaFree(ctx->d_ulen); cudaFree(ctx->d_counts);
     cudaFree(ctx->d_round_of); cudaFree(ctx->d_mm_of); cudaFree(ctx->d_ref_of); cudaFree(ctx->d_pos_of);
     cudaFree(ctx->d_ctr); cudaFree(ctx->d_len_hist); cudaFree(ctx->d_todo[0]); cudaFree(ctx->d_todo[1]);
-    cudaFree(ctx->d_todo_n); cudaFree(ctx->d_round_stats);
+    cudaFree(ctx->d_todo_n); cudaFree(ctx->d_round_stats); cudaFree(ctx->d_annot);
     cudaFree(ctx->d_mir_quant); cudaFree(ctx->d_mir_iscan); cudaFree(ctx->d_lib_totals); cudaFree(ctx->d_tally);
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -504,6 +509,11 @@ static int feed_regions(mirge_ctx *ctx, int sample, unsigned char *d_text, uint6
           { ProfScope p1(ctx, KID_K1_SLOW, 0);
             k1_slow_search<W><<<wave_grid(k1_slow_search<W>, K1_THREADS, rec_bound), K1_THREADS, 0, st>>>(sample, ctx->tp, ctx->thr, T, kc, Q,
                                                             (ctx->force_slow & 2) ? 1 : 0); } }
+        if (ctx->annotate_while_feeding && ctx->libs[MIRGE_LIB_MIRNA].total && !last) {
+            // the rounds of this region's new sequences run while the next region is being copied
+            int rc = annotate_impl<W>(ctx);
+            if (rc) return rc;
+        }
     }
     CK(cudaGetLastError());
     ctx->annotated = false; ctx->tallied = false;
@@ -655,6 +665,7 @@ static int load_library_impl(mirge_ctx *ctx, int lib_id, int n_refs, const char 
     CK(cudaStreamSynchronize(st));
     cudaFree(d_ascii);
     CK(cudaGetLastError());
+    { int rc = annot_clear(ctx); if (rc) return rc; }          // a library changed: every sequence is looked at again
     ctx->annotated = false; ctx->tallied = false;
     return MIRGE_OK;
 }
@@ -776,16 +787,38 @@ static const RoundSpec ROUNDS[MIRGE_N_ROUNDS] = {
     {MIRGE_LIB_SPIKEIN, 0, 0, 0, 0, 0, 0, 0},        // spike-in -n 0
 };
 
-template <int W>
-static int annotate_impl(mirge_ctx *ctx)
+// Annotation is incremental: dense ids are handed out in arrival order, so "the sequences not looked at yet" is the id
+// range [annot[0], n_unique).  k2_take_range claims it on the device (no host round trip); the rounds then run on that
+// range only.  With MIRGE_OPT_ANNOTATE_WHILE_FEEDING the rounds of region r run while the copy of region r+1 is in
+// flight, so at the end of a feed only the last region's sequences are left for mirge_annotate.
+__global__ void k2_take_range(const u64 *n_unique, u64 max_unique, u64 *annot)
+{
+    u64 hi = *n_unique;
+    if (hi > max_unique) hi = max_unique;
+    u64 lo = annot[0];
+    if (lo > hi) lo = hi;
+    annot[1] = lo; annot[2] = hi - lo; annot[0] = hi;
+}
+
+static int annot_clear(mirge_ctx *ctx)
 {
     cudaStream_t st = ctx->stream;
     CK(cudaMemsetAsync(ctx->d_round_of, 0, ctx->max_unique, st));
     CK(cudaMemsetAsync(ctx->d_mm_of, 0, ctx->max_unique, st));              // exports are deterministic for un-annotated sequences too
     CK(cudaMemsetAsync(ctx->d_ref_of, 0, ctx->max_unique * sizeof(int), st));
     CK(cudaMemsetAsync(ctx->d_pos_of, 0, ctx->max_unique * sizeof(int), st));
-    CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 1) * sizeof(u64), st));
     CK(cudaMemsetAsync(ctx->d_round_stats, 0, 2 * MIRGE_N_ROUNDS * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_annot, 0, 4 * sizeof(u64), st));
+    return MIRGE_OK;
+}
+
+template <int W>
+static int annotate_impl(mirge_ctx *ctx)
+{
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 1) * sizeof(u64), st));
+    k2_take_range<<<1, 1, 0, st>>>(ctx->d_ctr, ctx->max_unique, ctx->d_annot);
+    ctx->n_launches++;
     K2Arrays A;
     A.useq = ctx->d_useq; A.unmask = ctx->d_unmask; A.ulen = ctx->d_ulen;
     A.round_of = ctx->d_round_of; A.ref_of = ctx->d_ref_of; A.pos_of = ctx->d_pos_of; A.mm_of = ctx->d_mm_of;
@@ -800,13 +833,13 @@ static int annotate_impl(mirge_ctx *ctx)
         R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs; R.chunked = (ctx->force_slow & 0x1000) ? 1 : 0;   // per-tile appends measured faster for the heavy rounds
         for (int t = 0; t < l.ntabs; t++) { R.tabs[t].k = l.tab_k[t]; R.tabs[t].bucket_off = l.tab_off[t]; R.tabs[t].pos = l.tab_pos[t]; }
         const u32 *todo_in = r == 0 ? nullptr : ctx->d_todo[(r - 1) & 1];
-        const u64 *n_in = r == 0 ? ctx->d_ctr : ctx->d_todo_n + r;
+        const u64 *n_in = r == 0 ? ctx->d_annot + 2 : ctx->d_todo_n + r;
         ProfScope ps(ctx, KID_K2_ROUND0 + r);
         if (rs.param > 0 && rs.lib == MIRGE_LIB_MIRNA)      // several seeds over consecutive table sizes: balance them
-            k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+            k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_annot + 1, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else
-            k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+            k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_annot + 1, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
                                                        ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
     }
     CK(cudaGetLastError());
@@ -822,6 +855,12 @@ int mirge_annotate(mirge_ctx *ctx)
         if (rc) return rc;
     }
     return ctx->W == 2 ? annotate_impl<2>(ctx) : annotate_impl<4>(ctx);
+}
+
+int mirge_set_option(mirge_ctx *ctx, int option, int value)
+{
+    if (option == MIRGE_OPT_ANNOTATE_WHILE_FEEDING) { ctx->annotate_while_feeding = value != 0; return MIRGE_OK; }
+    return fail(ctx, MIRGE_E_ARG, "mirge_set_option: unknown option");
 }
 
 // ---------------------------------------------------------------------------
@@ -1053,6 +1092,7 @@ int mirge_reset_unique(mirge_ctx *ctx)
     // count rows at or beyond the unique counter were never touched since the last clear
     k1_clear_counts<<<grid_for(ctx->max_unique * (u64)ctx->S, 256, 148 * 8), 256, 0, st>>>(ctx->d_counts, ctx->d_ctr, ctx->max_unique, ctx->S);
     CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(u64), st));
+    { int rc = annot_clear(ctx); if (rc) return rc; }          // ids start again at 0: nothing is annotated
     ctx->annotated = false; ctx->tallied = false;
     return MIRGE_OK;
 }

@@ -113,6 +113,10 @@ class Engine:
     def annotate(self):
         self._ck(lib.mirge_annotate(self.h))
 
+    def annotate_while_feeding(self, on=True):
+        """Run the mapping rounds region by region inside feed_fastq (they hide behind the H2D copies)."""
+        self._ck(lib.mirge_set_option(self.h, 1, int(on)))
+
     # -- genome passes ------------------------------------------------------------
     def load_genome(self, names, seqs):
         """index.Libs/<sp>_genome (library slot 8)."""

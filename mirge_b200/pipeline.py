@@ -248,6 +248,8 @@ class AnnotateRun:
         for t in self.libdir.types:
             names, seqs = self.libdir.load(t)
             e.load_library(LIB_IDS[t], names, seqs)
+        if self.world == 1 and hasattr(e, 'annotate_while_feeding'):
+            e.annotate_while_feeding(True)      # no exchange follows: the rounds hide behind the copies
         self.engine = e
 
     # -- reference-shaped stages ------------------------------------------------

@@ -153,7 +153,45 @@ def annot_columns(uniq, lib_names, spike_in):
 
 def write_mapped_unmapped(outdir, uniq, lib_names, annot_name_list, sample_names, spike_in):
     """mapped.csv / unmapped.csv (writeDataToCSV.py:582-619,1172-1188).  Row order is
-    Python-2 dict order in the reference, i.e. unspecified; rows here follow unique id."""
+    Python-2 dict order in the reference, i.e. unspecified; rows here follow unique id.
+    Millions of rows: the columns are assembled as Arrow arrays straight from the exported buffers (no per-row Python
+    objects) and written by Arrow's multi-threaded CSV writer; pandas is the fallback for names that need quoting."""
+    try:
+        _write_mapped_unmapped_arrow(outdir, uniq, lib_names, annot_name_list, sample_names, spike_in)
+    except Exception:
+        _write_mapped_unmapped_pandas(outdir, uniq, lib_names, annot_name_list, sample_names, spike_in)
+
+
+def _write_mapped_unmapped_arrow(outdir, uniq, lib_names, annot_name_list, sample_names, spike_in):
+    import pyarrow as pa
+    import pyarrow.csv as pc
+    U = len(uniq['round_of'])
+    lens = uniq['len'].astype(np.int64)
+    raw = uniq['seq'].view(np.uint8).reshape(U, -1) if U else np.zeros((0, 1), np.uint8)
+    offsets = np.zeros(U + 1, np.int32)
+    np.cumsum(lens, out=offsets[1:])
+    data = raw[np.arange(raw.shape[1])[None, :] < lens[:, None]]
+    cols = {'uniqueSequence': pa.Array.from_buffers(pa.string(), U, [None, pa.py_buffer(offsets), pa.py_buffer(np.ascontiguousarray(data))]),
+            'annotFlag': pa.array((uniq['round_of'] > 0).astype(np.int64))}
+    n_slots = 10 if spike_in else 9
+    for slot, name in zip(range(1, n_slots + 1), annot_name_list):
+        hit = uniq['round_of'] == slot
+        idx = np.where(hit, uniq['ref_of'], 0).astype(np.int32)
+        names = pa.array([str(x) for x in lib_names.get(ROUND_LIB[slot - 1], [])] or [''], type=pa.string())
+        cols[name] = pa.DictionaryArray.from_arrays(pa.array(idx, mask=~hit), names).cast(pa.string())
+    for i, s_ in enumerate(sample_names):
+        cols[s_] = pa.array(np.ascontiguousarray(uniq['counts'][:, i]))
+    tab = pa.table(cols)
+    header = (','.join(['uniqueSequence', 'annotFlag'] + list(annot_name_list) + list(sample_names)) + '\n').encode()
+    mapped = pa.array(uniq['round_of'] > 0)
+    opts = pc.WriteOptions(include_header=False, quoting_style='none')
+    for fn, mask in (('mapped.csv', mapped), ('unmapped.csv', pa.compute.invert(mapped))):
+        with open(os.path.join(outdir, fn), 'wb') as f:
+            f.write(header)
+            pc.write_csv(tab.filter(mask), f, opts)
+
+
+def _write_mapped_unmapped_pandas(outdir, uniq, lib_names, annot_name_list, sample_names, spike_in):
     import pandas as pd
     cols = annot_columns(uniq, lib_names, spike_in)
     flag = (uniq['round_of'] > 0).astype(np.int64)

@@ -89,3 +89,32 @@ def test_report_row_and_spikein_header_quirk():
     hdr, row = rep.strip().split('\n')
     assert len(row.split(',')) == len(hdr.split(',')) + 1      # the header never gains the spike-in column
     assert rep == O.annotation_report_csv(['a.fastq'], log, True)
+
+
+def test_arrow_and_pandas_writers_of_mapped_csv_agree(tmp_path):
+    """mapped.csv / unmapped.csv: the Arrow writer used for millions of rows gives the bytes pandas gives."""
+    import os
+    import numpy as np
+    from mirge_b200 import tables
+    rng = np.random.default_rng(1)
+    U = 5000
+    lens = rng.integers(16, 64, U).astype(np.uint8)
+    raw = np.zeros((U, 64), np.uint8)
+    for i in range(U):
+        raw[i, :lens[i]] = rng.choice(np.frombuffer(b'ACGTN', np.uint8), lens[i])
+    uniq = dict(seq=raw.view('S64').reshape(U), len=lens, counts=rng.integers(0, 1000, (U, 2)).astype(np.uint32),
+                round_of=rng.integers(0, 11, U).astype(np.int8), ref_of=rng.integers(0, 50, U).astype(np.int32))
+    lib_names = {k: ['n%d_%d' % (k, j) for j in range(50)] for k in range(10)}
+    for spike in (False, True):
+        names = ['exact miRNA', 'hairpin miRNA', 'mature tRNA', 'primary tRNA', 'snoRNA', 'rRNA', 'ncrna others', 'mRNA', 'isomiR miRNA'] \
+            + (['spike-in'] if spike else [])
+        u = dict(uniq)
+        if not spike:
+            u['round_of'] = np.minimum(uniq['round_of'], 9).astype(np.int8)
+        a, b = tmp_path / ('a%d' % spike), tmp_path / ('b%d' % spike)
+        a.mkdir()
+        b.mkdir()
+        tables._write_mapped_unmapped_arrow(str(a), u, lib_names, names, ['s1.fastq', 's2.fastq'], spike)
+        tables._write_mapped_unmapped_pandas(str(b), u, lib_names, names, ['s1.fastq', 's2.fastq'], spike)
+        for fn in ('mapped.csv', 'unmapped.csv'):
+            assert open(os.path.join(str(a), fn)).read() == open(os.path.join(str(b), fn)).read(), fn
