@@ -800,6 +800,14 @@ __global__ void k2_take_range(const u64 *n_unique, u64 max_unique, u64 *annot)
     annot[1] = lo; annot[2] = hi - lo; annot[0] = hi;
 }
 
+// the first round's to-do list: the claimed id range written out (the round kernels keep their register budget: one
+// more kernel argument cost k2_round eight registers and an eighth of its occupancy)
+__global__ void k2_fill_range(const u64 *annot, u32 *todo)
+{
+    const u64 base = annot[1], n = annot[2];
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) todo[i] = (u32)(base + i);
+}
+
 static int annot_clear(mirge_ctx *ctx)
 {
     cudaStream_t st = ctx->stream;
@@ -818,7 +826,8 @@ static int annotate_impl(mirge_ctx *ctx)
     cudaStream_t st = ctx->stream;
     CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 1) * sizeof(u64), st));
     k2_take_range<<<1, 1, 0, st>>>(ctx->d_ctr, ctx->max_unique, ctx->d_annot);
-    ctx->n_launches++;
+    k2_fill_range<<<148 * 4, 256, 0, st>>>(ctx->d_annot, ctx->d_todo[1]);
+    ctx->n_launches += 2;
     K2Arrays A;
     A.useq = ctx->d_useq; A.unmask = ctx->d_unmask; A.ulen = ctx->d_ulen;
     A.round_of = ctx->d_round_of; A.ref_of = ctx->d_ref_of; A.pos_of = ctx->d_pos_of; A.mm_of = ctx->d_mm_of;
@@ -832,14 +841,14 @@ static int annotate_impl(mirge_ctx *ctx)
         R.round = r; R.len_filter = rs.len_filter; R.mode = rs.mode; R.param = rs.param; R.trim5 = rs.trim5; R.trim3 = rs.trim3;
         R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs; R.chunked = (ctx->force_slow & 0x1000) ? 1 : 0;   // per-tile appends measured faster for the heavy rounds
         for (int t = 0; t < l.ntabs; t++) { R.tabs[t].k = l.tab_k[t]; R.tabs[t].bucket_off = l.tab_off[t]; R.tabs[t].pos = l.tab_pos[t]; }
-        const u32 *todo_in = r == 0 ? nullptr : ctx->d_todo[(r - 1) & 1];
+        const u32 *todo_in = ctx->d_todo[(r + 1) & 1];             // round 0 reads the range list in d_todo[1]
         const u64 *n_in = r == 0 ? ctx->d_annot + 2 : ctx->d_todo_n + r;
         ProfScope ps(ctx, KID_K2_ROUND0 + r);
         if (rs.param > 0 && rs.lib == MIRGE_LIB_MIRNA)      // several seeds over consecutive table sizes: balance them
-            k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_annot + 1, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+            k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else
-            k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_annot + 1, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+            k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
                                                        ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
     }
     CK(cudaGetLastError());
