@@ -934,7 +934,7 @@ int mirge_tally(mirge_ctx *ctx)
       k3_seg_chunks<<<(n_seg + 1 + 255) / 256, 256, 0, st>>>(seg_start, seg_end, n_seg, chunk_off);
       ctx->n_launches += device_excl_scan(chunk_off, chunk_off, (u64)n_seg + 1, scratch, st);
       k3_chunk_reduce<<<grid_for((u64)max_chunks * 32, 256, 148 * 8), 256, 0, st>>>(vals[cur], seg_start, seg_end, chunk_off, n_seg,
-                                                                                   ctx->d_counts, ctx->d_round_of, S, partial);
+                                                                                   ctx->d_counts, ctx->d_round_of, S, ctx->max_unique, partial);
       k3_seg_reduce<<<grid_for((u64)n_seg * 32, 256, 148 * 8), 256, 0, st>>>(partial, chunk_off, n_seg, S, seg_q, seg_i, seg_u); }
     { ProfScope ps(ctx, KID_K3_FINAL);
       k3_finalize<<<S, 256, 0, st>>>(seg_q, seg_i, seg_u, n_mir, S, ctx->d_mir_quant, ctx->d_mir_iscan, ctx->d_lib_totals); }
@@ -946,6 +946,12 @@ int mirge_tally(mirge_ctx *ctx)
 // ---------------------------------------------------------------------------
 // export
 // ---------------------------------------------------------------------------
+__global__ void k_counts_rows(const u32 *__restrict__ counts, u64 cstride, u64 U, int S, u32 *__restrict__ out)
+{
+    for (u64 it = (u64)blockIdx.x * blockDim.x + threadIdx.x; it < U * (u64)S; it += (u64)gridDim.x * blockDim.x)
+        out[it] = counts[(it % S) * cstride + it / S];
+}
+
 // out[u * stride + i] = base i of unique u as ASCII (N for ambiguous), zero beyond its length
 template <int W>
 __global__ void k_unpack_unique(const u64 *__restrict__ useq, const u64 *__restrict__ unmask, const u8 *__restrict__ ulen, u64 U, int stride,
@@ -990,7 +996,17 @@ int mirge_export_unique(mirge_ctx *ctx, uint64_t cap, int stride, char *seq, uin
         cudaFree(d_out);
         if (e != cudaSuccess) { ctx->err = std::string("mirge_export_unique failed: ") + cudaGetErrorString(e); return MIRGE_E_CUDA; }
     }
-    if (counts) CK(cudaMemcpy(counts, ctx->d_counts, U * ctx->S * sizeof(u32), cudaMemcpyDeviceToHost));
+    if (counts && U) {
+        // device layout is a column per sample; the caller gets counts[u][s]
+        u32 *d_t = nullptr;
+        CK(cudaMalloc(&d_t, (size_t)U * ctx->S * sizeof(u32)));
+        ctx->n_launches++;
+        k_counts_rows<<<grid_for(U * (u64)ctx->S, 256, 148 * 16), 256, 0, ctx->stream>>>(ctx->d_counts, ctx->max_unique, U, ctx->S, d_t);
+        cudaError_t e = cudaMemcpyAsync(counts, d_t, (size_t)U * ctx->S * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_t);
+        if (e != cudaSuccess) { ctx->err = std::string("mirge_export_unique failed: ") + cudaGetErrorString(e); return MIRGE_E_CUDA; }
+    }
     if (ctx->annotated) {
         if (round_of) CK(cudaMemcpy(round_of, ctx->d_round_of, U, cudaMemcpyDeviceToHost));
         if (ref_of) CK(cudaMemcpy(ref_of, ctx->d_ref_of, U * sizeof(int), cudaMemcpyDeviceToHost));
@@ -1099,7 +1115,7 @@ int mirge_reset_unique(mirge_ctx *ctx)
     ProfScope ps(ctx, KID_RESET);
     CK(cudaMemsetAsync(ctx->d_slots, 0, ctx->table_cap * esz, st));
     // count rows at or beyond the unique counter were never touched since the last clear
-    k1_clear_counts<<<grid_for(ctx->max_unique * (u64)ctx->S, 256, 148 * 8), 256, 0, st>>>(ctx->d_counts, ctx->d_ctr, ctx->max_unique, ctx->S);
+    k1_clear_counts<<<grid_for(ctx->max_unique, 256, 148 * 8), 256, 0, st>>>(ctx->d_counts, ctx->d_ctr, ctx->max_unique, ctx->S);
     CK(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(u64), st));
     { int rc = annot_clear(ctx); if (rc) return rc; }          // ids start again at 0: nothing is annotated
     ctx->annotated = false; ctx->tallied = false;

@@ -584,7 +584,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
         bool lead; u32 id, cnt;
         table_find_warp<W>(T, p, nf, keep, keep ? pseq_hash<W>(p, nf) : 0ull, lead, id, cnt);
         if (force_slow & 0x100) { }                                        // diagnostic: no count updates
-        else if (force_slow & 0x800) { if (lead) atomicAdd(&T.counts[(u64)id * T.S + sample], cnt); }   // count cache off
+        else if (force_slow & 0x800) { if (lead) atomicAdd(&T.counts[(u64)sample * T.max_unique + id], cnt); }   // count cache off
         else count_cached<W>(cid, ccnt, T, sample, lead, id, cnt);
         if (keep) { atomicAdd(&wh[nf], 1u); my_kept++; }
     }

@@ -153,7 +153,7 @@ __global__ void k3_seg_chunks(const u32 *__restrict__ seg_start, const u32 *__re
 __global__ void __launch_bounds__(256)
 k3_chunk_reduce(const u32 *__restrict__ vals, const u32 *__restrict__ seg_start, const u32 *__restrict__ seg_end,
                 const u32 *__restrict__ chunk_off, int n_seg, const u32 *__restrict__ counts,
-                const signed char *__restrict__ round_of, int S, i64 *__restrict__ partial)
+                const signed char *__restrict__ round_of, int S, u64 cstride, i64 *__restrict__ partial)
 {
     const unsigned lane = threadIdx.x & 31;
     const u32 total = chunk_off[n_seg];
@@ -168,7 +168,7 @@ k3_chunk_reduce(const u32 *__restrict__ vals, const u32 *__restrict__ seg_start,
             i64 q = 0, qi = 0, qu = 0;
             for (u32 x = a + lane; x < b; x += 32) {
                 const u32 id = vals[x];
-                const u32 c = counts[(u64)id * S + s];
+                const u32 c = counts[(u64)s * cstride + id];             // counts[S][max_unique]
                 q += c;
                 if (round_of[id] == 1) qi += c;
                 qu += (c != 0);

@@ -124,4 +124,23 @@ if 'c4' in which:
     t_exp = time.perf_counter() - t0
     print(json.dumps({'config': 'C4 device part', 'reads': 2 * n, 'unique': int(len(uniq['len'])), 'device_e2e_ms': t_dev * 1e3,
                       'reads_per_s': 2 * n / t_dev, 'export_unique_s': t_exp}), flush=True)
+    # the -ai genome passes on every miRNA-annotated unique sequence (writeDataToCSV.py:1260: -n 1 -a -3 2) and the
+    # -n 0 variant (:1488), against a 10^8-nt genome
+    gn, gs = world.genome(total=100_000_000, n_chrom=8)
+    t0 = time.perf_counter()
+    e.load_genome(gn, gs)
+    e.sync()
+    t_idx = time.perf_counter() - t0
+    ids = np.nonzero((uniq['round_of'] == 1) | (uniq['round_of'] == 9))[0].astype(np.uint32)
+    out = {}
+    for label, nmm in (('n1', 1), ('n0', 0)):
+        e.genome_pass_ids(ids[:1000], 0, nmm, 28, 2)
+        t0 = time.perf_counter()
+        c = e.genome_pass_ids(ids, 0, nmm, 28, 2)
+        dt = time.perf_counter() - t0
+        occ = c.sum(axis=1)
+        out[label] = {'pass_ms': dt * 1e3, 'queries_per_s': len(ids) / dt, 'aligned': int((occ > 0).sum()), 'alignments': int(c.sum())}
+    best_unique = int(((c[:, 0] == 1) | ((c[:, 0] == 0) & (c[:, 1] == 1))).sum())
+    print(json.dumps({'config': 'C4 genome passes (-ai)', 'genome_nt': sum(len(x) for x in gs), 'index_build_s': t_idx, 'queries': int(len(ids)),
+                      **{k + '_' + kk: vv for k, v in out.items() for kk, vv in v.items()}}), flush=True)
     e.close()
