@@ -39,6 +39,7 @@ static const char *KERNEL_NAMES[MIRGE_N_KERNELS] = {
 
 struct DevLib {
     u32 max_ref_len = 0;
+    int has_amb = 0;
     u64 *seq = nullptr, *amb = nullptr;
     u32 *ref_off = nullptr, *blk_ref = nullptr;
     int n_refs = 0;
@@ -584,6 +585,8 @@ static int load_library_impl(mirge_ctx *ctx, int lib_id, int n_refs, const char 
     CK(cudaMemsetAsync(l.amb, 0, (nw64 + 8) * sizeof(u64), st));
     std::vector<u32> off32(n_refs + 1);
     for (int i = 0; i <= n_refs; i++) off32[i] = (u32)(n_refs ? offsets[i] : 0);
+    l.has_amb = 0;
+    for (u64 i = 0; i < total && !l.has_amb; i++) if (base_code((unsigned char)seq_ascii[i]) > 3) l.has_amb = 1;
     l.max_ref_len = 0;
     for (int i = 0; i < n_refs; i++) if (off32[i + 1] - off32[i] > l.max_ref_len) l.max_ref_len = off32[i + 1] - off32[i];
     CK(cudaMalloc(&l.ref_off, (size_t)(n_refs + 1) * sizeof(u32)));
@@ -604,7 +607,7 @@ static int load_library_impl(mirge_ctx *ctx, int lib_id, int n_refs, const char 
     CK(cudaMalloc(&d_ascii, total));
     CK(cudaMemcpyAsync(d_ascii, seq_ascii, total, cudaMemcpyHostToDevice, st));
     k2_pack_library<<<(unsigned)((nw64 + 127) / 128), 128, 0, st>>>(d_ascii, (u32)total, l.seq, l.amb);
-    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = n_refs; L.total = (u32)total; L.max_ref_len = l.max_ref_len;
+    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = n_refs; L.total = (u32)total; L.max_ref_len = l.max_ref_len; L.has_amb = l.has_amb;
     if (lib_id == MIRGE_LIB_GENOME) {
         // one prefix-ordered table: kmax-mers, first base most significant (k2_genome.cuh)
         int kmax = 6;
@@ -687,7 +690,7 @@ static int genome_pass_run(mirge_ctx *ctx, uint64_t n, const u64 *qs, const u64 
 {
     cudaStream_t st = ctx->stream;
     const DevLib &l = ctx->libs[MIRGE_LIB_GENOME];
-    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = l.n_refs; L.total = l.total; L.max_ref_len = l.max_ref_len;
+    LibView L; L.seq = l.seq; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = l.n_refs; L.total = l.total; L.max_ref_len = l.max_ref_len; L.has_amb = l.has_amb;
     GenomeIndex X; X.off = l.gx_off; X.pos = l.gx_pos; X.kmax = l.gx_kmax;
     u32 *d_counts = nullptr;
     CK(cudaMalloc(&d_counts, (size_t)n * 4 * sizeof(u32)));
@@ -835,7 +838,7 @@ static int annotate_impl(mirge_ctx *ctx)
     for (int r = 0; r < nrounds; r++) {
         const RoundSpec &rs = ROUNDS[r];
         const DevLib &l = ctx->libs[rs.lib];
-        LibView L; L.seq = l.total ? l.seq : nullptr; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = l.n_refs; L.total = l.total; L.max_ref_len = l.max_ref_len;
+        LibView L; L.seq = l.total ? l.seq : nullptr; L.amb = l.amb; L.ref_off = l.ref_off; L.blk_ref = l.blk_ref; L.n_refs = l.n_refs; L.total = l.total; L.max_ref_len = l.max_ref_len; L.has_amb = l.has_amb;
         RoundParams R;
         memset(&R, 0, sizeof R);
         R.round = r; R.len_filter = rs.len_filter; R.mode = rs.mode; R.param = rs.param; R.trim5 = rs.trim5; R.trim3 = rs.trim3;

@@ -133,7 +133,7 @@ template <int W>
 __device__ __forceinline__ bool diff_at(const LibView &L, const Query<W> &q, u32 g, u64 *d)
 {
     if ((u64)g + (u64)q.n > (u64)L.total) return false;
-    {
+    if (L.has_amb) {
         const u32 wi = g >> 6, sh = g & 63;
         int rem = q.n;
 #pragma unroll

@@ -24,6 +24,7 @@ struct LibView {
     int n_refs;
     u32 total;
     u32 max_ref_len;       // longest entry: a longer query has no placement
+    int has_amb;           // some base of the library is not A, C, G, T (else the ambiguity windows need not be read)
 };
 
 struct KmerTab {
@@ -109,7 +110,7 @@ __device__ __forceinline__ bool verify_at(const LibView &L, const Query<W> &q, u
 {
     if ((u64)g + (u64)q.n > (u64)L.total) return false;
     // ambiguity window
-    {
+    if (L.has_amb) {
         const u32 wi = g >> 6, sh = g & 63;
         int rem = q.n;
 #pragma unroll
