@@ -60,8 +60,10 @@ __device__ __forceinline__ void st_release_u32(u32 *p, u32 v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// Key compare of a published entry; the id rides along in the same round trip (it shares a 16-byte unit with the
+// tag), so a hit costs the tag load plus ONE more access to the sector.
 template <int W>
-__device__ __forceinline__ bool entry_key_equal(const TEntry<W> *e, const PSeq<W> &k)
+__device__ __forceinline__ bool entry_key_equal(const TEntry<W> *e, const PSeq<W> &k, u32 &id_out)
 {
     bool eq = true;
 #pragma unroll
@@ -70,8 +72,18 @@ __device__ __forceinline__ bool entry_key_equal(const TEntry<W> *e, const PSeq<W
         ldcg_u64x2(&e->s[w], a, b);
         eq = eq && (a == k.s[w]) && (b == k.s[w + 1]);
     }
-#pragma unroll
-    for (int w = 0; w < W / 2; w++) eq = eq && (ldcg_u64(&e->nm[w]) == k.nm[w]);
+    if (W == 2) {
+        u64 c, d;
+        ldcg_u64x2(&e->nm[0], c, d);            // nm | tag, id
+        eq = eq && (c == k.nm[0]);
+        id_out = (u32)(d >> 32);
+    } else {
+        u64 c, d, t, pad;
+        ldcg_u64x2(&e->nm[0], c, d);
+        ldcg_u64x2(&e->tag, t, pad);
+        eq = eq && (c == k.nm[0]) && (d == k.nm[W / 2 - 1]);
+        id_out = (u32)(t >> 32);
+    }
     return eq;
 }
 
@@ -135,8 +147,9 @@ __device__ __forceinline__ void table_find_warp(const TableView<W> &T, const PSe
                 }
                 if ((t | 1u) == (want | 1u)) {
                     if (!(t & 1u)) break;                               // unpublished: look again after this warp's own publishes
-                    if (entry_key_equal<W>(e, key)) {
-                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(id) : "l"(&e->id) : "memory");
+                    u32 eid;
+                    if (entry_key_equal<W>(e, key, eid)) {
+                        id = eid;
                         state = 0;
                         break;
                     }

@@ -40,6 +40,21 @@ try:
         r = orig_write(self, *a, **k)
         stages['export_and_tables_s'] = time.perf_counter() - t
         return r
+    orig_new, orig_trim = P.AnnotateRun._new_engine, P.AnnotateRun.trim_file
+
+    def new_engine(self):
+        t = time.perf_counter()
+        r = orig_new(self)
+        self.engine.sync()
+        stages['create_engine_load_libraries_s'] = stages.get('create_engine_load_libraries_s', 0.0) + time.perf_counter() - t
+        return r
+
+    def trim_file(self, *a, **k):
+        t = time.perf_counter()
+        r = orig_trim(self, *a, **k)
+        stages['read_file_feed_s'] = stages.get('read_file_feed_s', 0.0) + time.perf_counter() - t
+        return r
+    P.AnnotateRun._new_engine, P.AnnotateRun.trim_file = new_engine, trim_file
     P.AnnotateRun.run, P.AnnotateRun.write_outputs = run, write_outputs
     t0 = time.perf_counter()
     out = main(['annotate', '-s', fq, '-o', root, '-lib', os.path.join(root, 'libs'), '-sp', 'synth', '-ad', 'illumina'])
