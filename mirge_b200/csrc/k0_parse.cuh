@@ -39,7 +39,7 @@
 #define K0_TILE 16384
 #define K0_HALO 1024
 #define K0_UNITS ((K0_TILE + K0_HALO) / 16)
-#define K0_RPP 256                  // records per pass: one per thread in the per-record phases
+#define K0_RPP 160                  // records per pass: one per thread in the per-record phases
 #define K0_CAP (4 * K0_RPP + 4)      // line-start list entries per pass
 #define K0_MW (K0_TILE / K0_THREADS / 32)   // 32-bit newline-mask words of the bytes one thread ranks
 #define K0_NONE 0xFFFFu             // list entry: the line starts before the halo
@@ -436,7 +436,7 @@ __device__ __forceinline__ u32 k0_test_candidate(const unsigned char *buf, const
 // region only).  info[t] = newline count of tile t | claim << 20.  state->nrec and state->err_spec
 // are zeroed before the launch.
 template <int W>
-__global__ void __launch_bounds__(K0_THREADS)
+__global__ void __launch_bounds__(K0_THREADS, 8)
 k0_parse_spec(const unsigned char *__restrict__ text, u64 reg_start, u64 reg_end, int vnl, u32 ntiles,
               u32 *__restrict__ info, K0State *__restrict__ state, K0Params prm, u64 rec_cap,
               u64 *__restrict__ bases, u64 *__restrict__ nmask, u32 *__restrict__ meta)
