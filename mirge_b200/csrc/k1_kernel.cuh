@@ -526,7 +526,7 @@ __device__ __forceinline__ void k1_teardown(u32 my_kept, u32 my_diag, u64 *diag,
 // 2 = ... through the literal DP instead, 4 = prefilter off.
 #define K1A_THREADS 256
 template <int W>
-__global__ void __launch_bounds__(K1A_THREADS)
+__global__ void __launch_bounds__(K1A_THREADS, 6)
 k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
                  const u64 *__restrict__ n_records_ptr, int sample, TrimParams tp_param, K1Pre pre_param, K1Thr thr_param,
                  TableView<W> T, K1Counters ctr, K1Queues Q, int force_slow)
