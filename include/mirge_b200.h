@@ -197,12 +197,13 @@ int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const cha
 /* Test hook: force_slow = 1 sends every read through the slow queue (all-column
  * bit-vector search), 3 through the literal banded cutadapt DP, 4 switches the
  * exact-match prefilter off (every read takes the windowed bit-vector search),
+ * 0x2000 parses FASTQ with the exact chained-scan kernel only (no speculation),
  * 0 restores the default, -1 leaves the setting unchanged; slow_reads (may be
  * NULL) receives the number of reads that went through the slow queue so far.
  * Results are identical in every mode. */
 int mirge_debug(mirge_ctx *ctx, int force_slow, uint64_t *slow_reads);
 /* Diagnostics since the last reset: out4 = reads through the all-column search,
- * reads the prefilter sent to the full-candidate scan (class 1), reads it sent
+ * reads of prefilter class 1 (settled or passed on by the piece filter), reads sent
  * to the general search (class 2), feed regions whose speculative parse was
  * rejected and redone by the exact kernel (k0_parse.cuh).  Synchronises. */
 int mirge_trim_classes(mirge_ctx *ctx, uint64_t *out4);

@@ -5,8 +5,9 @@
 //   2. find the 3' adapter exactly as cutadapt would:
 //        prefilter  - exact comparisons plus host-proved dominance tables settle most
 //                     reads with no dynamic programming at all (k1_prefilter.cuh);
-//        class 1    - reads that only need the full-length cost scan (score-only
-//                     Myers columns);
+//        class 1    - reads for which only a full-length candidate in a bounded column range
+//                     could outrank the exact prefix: settled in place by the pigeonhole
+//                     piece filter (k1_piece_hit), no dynamic programming either;
 //        class 2    - general search: Myers' bit-vector edit distance (the <=32-nt
 //                     adapter is one machine word) gives the cost of EVERY DP cell of
 //                     the last columns; the few candidate end cells cutadapt ranks by
@@ -20,7 +21,7 @@
 //                     adapter occurrence, adapters > 32 nt): the same search with all
 //                     columns kept, or the literal banded DP (locate_back);
 //   3. length filter, then warp-collective insert into the unique-sequence table.
-// The classes run as four kernels connected by device queues (end of this file).
+// The classes run as three kernels connected by device queues of 32-byte read records (end of this file).
 // Every path returns cutadapt's rstart; parity tests compare them read by read.
 #pragma once
 #include "common.cuh"
@@ -526,7 +527,7 @@ __device__ __forceinline__ void k1_teardown(u32 my_kept, u32 my_diag, u64 *diag,
 // 2 = ... through the literal DP instead, 4 = prefilter off.
 #define K1A_THREADS 256
 template <int W>
-__global__ void __launch_bounds__(K1A_THREADS, 6)
+__global__ void __launch_bounds__(K1A_THREADS)
 k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, const u32 *__restrict__ meta,
                  const u64 *__restrict__ n_records_ptr, int sample, TrimParams tp_param, K1Pre pre_param, K1Thr thr_param,
                  TableView<W> T, K1Counters ctr, K1Queues Q, int force_slow)

@@ -22,9 +22,11 @@
 //   safe_len[I] bit l   no X at all                      -> class 0: rstart = n - l
 //   safe_p bit l        no X among the adapter prefixes at the read end, whatever
 //                       the insert; full-length X must end at a column
-//                       <= I + fullreach[l]             -> class 1: the read only
-//                       needs the bit-vector cost scan of those columns (no
-//                       candidate walks); no full-length candidate there -> rstart = n - l
+//                       <= I + fullreach[l]             -> class 1: no full-length
+//                       candidate in those columns -> rstart = n - l.  The kernel decides that
+//                       with the pigeonhole piece filter (k1_piece_hit below); the score-only
+//                       Myers scan (k1_full_candidate_scan) is the reference the host tests hold
+//                       the filter against
 //   otherwise                                            -> class 2: general search
 //
 // The search for FULL / E uses the adapter's first four bases as an anchor: all anchor
