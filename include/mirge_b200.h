@@ -132,8 +132,13 @@ int mirge_genome_pass_ids(mirge_ctx *ctx, uint64_t n, const uint32_t *ids, int m
  * mapping rounds on the sequences each 64 MiB region added while the next region
  * is being copied, so mirge_annotate only has the last region left -- the rounds
  * hide behind the host-to-device copies.  Libraries must be loaded before
- * feeding; leave it off when the table is rebuilt afterwards (multi-GPU exchange). */
-enum { MIRGE_OPT_ANNOTATE_WHILE_FEEDING = 1 };
+ * feeding; leave it off when the table is rebuilt afterwards (multi-GPU exchange).
+ * MIRGE_OPT_PAIR_SEEDS (default 16; read by mirge_load_library): short queries of
+ * the -n 1 / -v 1 / -v 2 rounds are searched through pair-of-pieces seed tables
+ * wherever the plain pigeonhole seeds would offer at least this many candidate
+ * placements per query; 1 = wherever such a table can serve, 0 = never.  The
+ * tables only shorten the candidate lists -- the alignments reported are the same. */
+enum { MIRGE_OPT_ANNOTATE_WHILE_FEEDING = 1, MIRGE_OPT_PAIR_SEEDS = 2 };
 int mirge_set_option(mirge_ctx *ctx, int option, int value);
 
 /* -- stage 3: tallies ----------------------------------------------------- */

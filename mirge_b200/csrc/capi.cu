@@ -50,6 +50,8 @@ struct DevLib {
     u32 *tab_pos[K2_MAX_TABS];
     u32 *gx_off = nullptr, *gx_pos = nullptr;     // genome slot: one prefix-ordered table for every seed length
     int gx_kmax = 0;
+    int ngap = 0;                                 // pair-of-pieces seed sets (k2_map.cuh:GapSet)
+    GapSet gap[4];
 };
 
 struct ProfSpan { int kid; cudaEvent_t a, b; };
@@ -91,6 +93,7 @@ struct mirge_ctx {
     u64 *d_round_stats = nullptr;   // [2][MIRGE_N_ROUNDS]
     bool annotated = false;
     bool annotate_while_feeding = false;
+    int pair_seeds = 16;                            // MIRGE_OPT_PAIR_SEEDS
     u64 *d_annot = nullptr;         // [0] ids annotated so far, [1] base and [2] size of the range being annotated
     // tallies
     i64 *d_mir_quant = nullptr, *d_mir_iscan = nullptr, *d_lib_totals = nullptr;
@@ -311,6 +314,7 @@ static void free_lib(DevLib &l)
     cudaFree(l.seq); cudaFree(l.amb); cudaFree(l.ref_off); cudaFree(l.blk_ref);
     for (int t = 0; t < l.ntabs; t++) { cudaFree(l.tab_off[t]); cudaFree(l.tab_pos[t]); }
     cudaFree(l.gx_off); cudaFree(l.gx_pos);
+    for (int g = 0; g < l.ngap; g++) { cudaFree((void *)l.gap[g].off); cudaFree((void *)l.gap[g].pos); }
     l = DevLib();
 }
 
@@ -565,6 +569,92 @@ int mirge_get_stats(mirge_ctx *ctx, uint64_t *processed, uint64_t *kept, uint64_
 // ---------------------------------------------------------------------------
 // libraries
 // ---------------------------------------------------------------------------
+struct RoundSpec { int lib, len_filter, mode, param, trim5, trim3, highest, polyT; };
+// runAnnotationPipeline.py:574-599
+static const RoundSpec ROUNDS[MIRGE_N_ROUNDS] = {
+    {MIRGE_LIB_MIRNA, -26, 0, 0, 0, 0, 0, 0},        // bowtie mirna -n 0, len < 26
+    {MIRGE_LIB_HAIRPIN, 25, 0, 1, 0, 0, 0, 0},       // hairpin -n 1, len > 25
+    {MIRGE_LIB_MATURE_TRNA, 0, 1, 1, 0, 0, 1, 0},    // mature tRNA -v 1 -a --best --strata
+    {MIRGE_LIB_PRE_TRNA, 0, 1, 0, 0, 0, 1, 1},       // pre-tRNA poly-T round, -v 0 -a --best --strata
+    {MIRGE_LIB_SNORNA, 0, 0, 1, 0, 0, 0, 0},         // snoRNA -n 1
+    {MIRGE_LIB_RRNA, 0, 0, 1, 0, 0, 0, 0},           // rRNA -n 1
+    {MIRGE_LIB_NCRNA_OTHERS, 0, 0, 1, 0, 0, 0, 0},   // ncRNA others -n 1
+    {MIRGE_LIB_MRNA, 0, 0, 0, 0, 0, 0, 0},           // mRNA -n 0
+    {MIRGE_LIB_MIRNA, 0, 1, 2, 1, 2, 0, 0},          // mirna -5 1 -3 2 -v 2 --best (isomiR)
+    {MIRGE_LIB_SPIKEIN, 0, 0, 0, 0, 0, 0, 0},        // spike-in -n 0
+};
+
+// One GapSet (k2_map.cuh): m pieces of pl bases, a table per pair of pieces, serving regions rg_lo .. rg_hi.
+static int build_gap_set(mirge_ctx *ctx, DevLib &l, const LibView &L, int m, int pl, int rg_lo, int rg_hi)
+{
+    cudaStream_t st = ctx->stream;
+    const int npairs = m * (m - 1) / 2;
+    const u64 nb1 = (1ull << (4 * pl)) + 1;
+    const u32 npos = l.total - (u32)(m * pl) + 1;
+    u32 *off = nullptr, *pos = nullptr, *cursor = nullptr, *scratch = nullptr;
+    cudaError_t e = cudaMalloc(&off, (size_t)npairs * nb1 * sizeof(u32));
+    if (e == cudaSuccess) e = cudaMalloc(&pos, (size_t)npairs * npos * sizeof(u32));
+    if (e == cudaSuccess) e = cudaMalloc(&cursor, nb1 * sizeof(u32));
+    if (e == cudaSuccess) e = cudaMalloc(&scratch, scan_scratch_elems(nb1) * sizeof(u32));
+    if (e == cudaSuccess) e = cudaMemsetAsync(off, 0, (size_t)npairs * nb1 * sizeof(u32), st);
+    for (int sd = 0; sd < npairs && e == cudaSuccess; sd++) {
+        const int grid = grid_for(npos, 256, 148 * 8);
+        const int oi = gap_piece(m, sd, 0) * pl, oj = gap_piece(m, sd, 1) * pl;
+        u32 *o = off + (size_t)sd * nb1;
+        k2_gap_pass<<<grid, 256, 0, st>>>(L, pl, oi, oj, npos, 0, o, nullptr);
+        device_excl_scan(o, o, nb1, scratch, st);
+        e = cudaMemcpyAsync(cursor, o, nb1 * sizeof(u32), cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) k2_gap_pass<<<grid, 256, 0, st>>>(L, pl, oi, oj, npos, 1, cursor, pos + (size_t)sd * npos);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(cursor); cudaFree(scratch);
+    if (e != cudaSuccess) {
+        cudaFree(off); cudaFree(pos);
+        ctx->err = std::string("pair seed table build failed: ") + cudaGetErrorString(e);
+        return MIRGE_E_CUDA;
+    }
+    GapSet &G = l.gap[l.ngap++];
+    G.m = m; G.pl = pl; G.rg_lo = rg_lo; G.rg_hi = rg_hi; G.nb1 = (u32)nb1; G.npos = npos; G.off = off; G.pos = pos;
+    return MIRGE_OK;
+}
+
+// Which regions a pair set should serve: those where the classic seeds (e + 1 pieces, longest table that fits) are
+// expected to offer at least `ctx->pair_seeds` candidates per query and clearly more than the pair tables do
+// (pair_seeds == 1: every region the set can serve).  Expected counts assume a random library.
+static int plan_gap_sets(mirge_ctx *ctx, DevLib &l, const LibView &L, int lib_id, const std::vector<int> &ks)
+{
+    if (ctx->pair_seeds <= 0) return MIRGE_OK;
+    for (int e = 1; e <= 2; e++) {
+        bool used = false;
+        for (int r = 0; r < MIRGE_N_ROUNDS; r++) if (ROUNDS[r].lib == lib_id && ROUNDS[r].param == e) used = true;
+        if (!used) continue;
+        const int m = e + 2, npairs = m * (m - 1) / 2;
+        const int pls[2] = {m == 4 ? 3 : 5, m == 4 ? 4 : 6};
+        for (int x = 0; x < 2; x++) {
+            const int pl = pls[x], lo = m * pl, hi_max = x == 0 ? m * pls[1] - 1 : 23;
+            if ((u64)l.total < (u64)lo) continue;
+            const double pair_c = (double)npairs * l.total / (double)(1ull << (4 * pl));
+            auto classic_k = [&](int rg) { int kc = -1; for (int k : ks) if (k <= rg / (e + 1) && (u64)k <= l.total) kc = k; return kc; };
+            int s_lo = -1, s_hi = -1;
+            for (int rg = lo; rg <= hi_max; rg++) {
+                const int kc = classic_k(rg);
+                const double classic_c = kc < 0 ? 0.0 : (double)(e + 1) * l.total / (double)(1ull << (2 * kc));
+                const bool serve = ctx->pair_seeds == 1 || (classic_c >= (double)ctx->pair_seeds && classic_c > 1.5 * pair_c + 2.0);
+                if (serve) { if (s_lo < 0) s_lo = rg; s_hi = rg; }
+                else if (s_lo >= 0) break;
+            }
+            if (s_lo < 0 || l.ngap >= 4) continue;
+            // regions no classic table fits (below 16 bases, only with a non-default min_length) would scan every offset:
+            // a set that exists anyway takes them too
+            while (s_lo > lo && classic_k(s_lo - 1) < 0) s_lo--;
+            int rc = build_gap_set(ctx, l, L, m, pl, s_lo, s_hi);
+            if (rc) return rc;
+        }
+    }
+    return MIRGE_OK;
+}
+
 static int load_library_impl(mirge_ctx *ctx, int lib_id, int n_refs, const char *seq_ascii, const uint64_t *offsets)
 {
     if (lib_id < 0 || lib_id >= MIRGE_N_LIBS || n_refs < 0 || (n_refs > 0 && (!seq_ascii || !offsets)))
@@ -668,6 +758,7 @@ static int load_library_impl(mirge_ctx *ctx, int lib_id, int n_refs, const char 
     CK(cudaStreamSynchronize(st));
     cudaFree(d_ascii);
     CK(cudaGetLastError());
+    { int rc = plan_gap_sets(ctx, l, L, lib_id, ks); if (rc) return rc; }
     { int rc = annot_clear(ctx); if (rc) return rc; }          // a library changed: every sequence is looked at again
     ctx->annotated = false; ctx->tallied = false;
     return MIRGE_OK;
@@ -775,20 +866,6 @@ int mirge_genome_pass_ids(mirge_ctx *ctx, uint64_t n, const uint32_t *ids, int m
     return rc;
 }
 
-struct RoundSpec { int lib, len_filter, mode, param, trim5, trim3, highest, polyT; };
-// runAnnotationPipeline.py:574-599
-static const RoundSpec ROUNDS[MIRGE_N_ROUNDS] = {
-    {MIRGE_LIB_MIRNA, -26, 0, 0, 0, 0, 0, 0},        // bowtie mirna -n 0, len < 26
-    {MIRGE_LIB_HAIRPIN, 25, 0, 1, 0, 0, 0, 0},       // hairpin -n 1, len > 25
-    {MIRGE_LIB_MATURE_TRNA, 0, 1, 1, 0, 0, 1, 0},    // mature tRNA -v 1 -a --best --strata
-    {MIRGE_LIB_PRE_TRNA, 0, 1, 0, 0, 0, 1, 1},       // pre-tRNA poly-T round, -v 0 -a --best --strata
-    {MIRGE_LIB_SNORNA, 0, 0, 1, 0, 0, 0, 0},         // snoRNA -n 1
-    {MIRGE_LIB_RRNA, 0, 0, 1, 0, 0, 0, 0},           // rRNA -n 1
-    {MIRGE_LIB_NCRNA_OTHERS, 0, 0, 1, 0, 0, 0, 0},   // ncRNA others -n 1
-    {MIRGE_LIB_MRNA, 0, 0, 0, 0, 0, 0, 0},           // mRNA -n 0
-    {MIRGE_LIB_MIRNA, 0, 1, 2, 1, 2, 0, 0},          // mirna -5 1 -3 2 -v 2 --best (isomiR)
-    {MIRGE_LIB_SPIKEIN, 0, 0, 0, 0, 0, 0, 0},        // spike-in -n 0
-};
 
 // Annotation is incremental: dense ids are handed out in arrival order, so "the sequences not looked at yet" is the id
 // range [annot[0], n_unique).  k2_take_range claims it on the device (no host round trip); the rounds then run on that
@@ -844,10 +921,19 @@ static int annotate_impl(mirge_ctx *ctx)
         R.round = r; R.len_filter = rs.len_filter; R.mode = rs.mode; R.param = rs.param; R.trim5 = rs.trim5; R.trim3 = rs.trim3;
         R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs; R.chunked = (ctx->force_slow & 0x1000) ? 1 : 0;   // per-tile appends measured faster for the heavy rounds
         for (int t = 0; t < l.ntabs; t++) { R.tabs[t].k = l.tab_k[t]; R.tabs[t].bucket_off = l.tab_off[t]; R.tabs[t].pos = l.tab_pos[t]; }
+        for (int g = 0; g < l.ngap; g++)
+            if (rs.param >= 1 && l.gap[g].m == rs.param + 2 && R.ngap < K2_MAX_GAPSETS) { R.gap[R.ngap++] = l.gap[g]; R.gap_pairs = l.gap[g].m * (l.gap[g].m - 1) / 2; }
         const u32 *todo_in = ctx->d_todo[(r + 1) & 1];             // round 0 reads the range list in d_todo[1]
         const u64 *n_in = r == 0 ? ctx->d_annot + 2 : ctx->d_todo_n + r;
         ProfScope ps(ctx, KID_K2_ROUND0 + r);
-        if (rs.param > 0 && rs.lib == MIRGE_LIB_MIRNA)      // several seeds over consecutive table sizes: balance them
+        const bool eight = !(ctx->force_slow & 0x4000);    // 8 CTAs/SM measured faster for both pair rounds (0.57 vs 0.94 ms, 0.81 vs 1.19 ms)
+        if (R.ngap > 0 && eight)                            // short queries go through the pair-of-pieces tables
+            k2_round_pairs8<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+                                                      ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
+        else if (R.ngap > 0)
+            k2_round_pairs<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+                                                      ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
+        else if (rs.param > 0 && rs.lib == MIRGE_LIB_MIRNA) // several seeds over consecutive table sizes: balance them
             k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else
@@ -872,6 +958,7 @@ int mirge_annotate(mirge_ctx *ctx)
 int mirge_set_option(mirge_ctx *ctx, int option, int value)
 {
     if (option == MIRGE_OPT_ANNOTATE_WHILE_FEEDING) { ctx->annotate_while_feeding = value != 0; return MIRGE_OK; }
+    if (option == MIRGE_OPT_PAIR_SEEDS) { ctx->pair_seeds = value < 0 ? 0 : value; return MIRGE_OK; }   // read when a library is loaded
     return fail(ctx, MIRGE_E_ARG, "mirge_set_option: unknown option");
 }
 

@@ -33,6 +33,28 @@ struct KmerTab {
     const u32 *pos;         // global base offsets grouped by k-mer
 };
 
+// Pair-of-pieces seed tables for short queries.  A round that tolerates e mismatches in its seed region cuts
+// the region's first m*pl bases into m = e + 2 pieces of pl bases: e mismatches leave at least TWO pieces
+// intact, so every valid placement is found under the key (piece i, piece j) of one of the m(m-1)/2 pairs.
+// A pair key holds 2*pl bases where the classic pigeonhole seed of the same region holds region/(e+1):
+// for a 16-base region and e = 2 that is 8 bases against 5, 64 times fewer candidates to verify.
+// One table per pair, indexed by placement start (the pieces sit at fixed offsets i*pl and j*pl).
+#define K2_MAX_GAPSETS 2
+struct GapSet {
+    int m, pl;           // pieces, piece length
+    int rg_lo, rg_hi;    // region lengths this set serves (rg_lo >= m*pl)
+    u32 nb1;             // 4^(2*pl) + 1: stride of the per-pair bucket arrays
+    u32 npos;            // placements per pair table: total - m*pl + 1
+    const u32 *off;      // [m(m-1)/2][nb1] offsets into the pair's own block of pos
+    const u32 *pos;      // [m(m-1)/2][npos] placement starts grouped by key
+};
+// piece indices of pair `sd` (which = 0: first piece, 1: second), m = 3 or 4, pairs in lexicographic order
+__host__ __device__ __forceinline__ int gap_piece(int m, int sd, int which)
+{
+    const u32 t = (m == 3) ? (which ? 0x221u : 0x100u) : (which ? 0x332321u : 0x211000u);
+    return (int)((t >> (4 * sd)) & 15u);
+}
+
 struct RoundParams {
     int round;          // 0-based round index; annot slot = round + 1
     int len_filter;     // <0: len < -f ; >0: len > f ; 0: all   (runAnnotationPipeline.py:574/588)
@@ -44,6 +66,8 @@ struct RoundParams {
     int ntabs;
     int chunked;        // to-do appends: 1 = chunk reservation per warp (lists hold padding), 0 = one atomic per warp and tile
     KmerTab tabs[K2_MAX_TABS];   // ascending k
+    int ngap, gap_pairs;         // pair-of-pieces sets for this round's mismatch budget, pairs per set
+    GapSet gap[K2_MAX_GAPSETS];
 };
 
 // ---------------------------------------------------------------------------
@@ -79,6 +103,17 @@ __global__ void k2_kmer_pass(LibView L, int k, int pass, u32 *__restrict__ bucke
     const u32 mask = (k == 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
     for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g + (u64)k <= (u64)L.total; g += (u64)gridDim.x * blockDim.x) {
         const u32 code = (u32)lib_window64(L.seq, (u32)g) & mask;
+        if (pass == 0) atomicAdd(&bucket[code], 1u);
+        else pos[atomicAdd(&bucket[code], 1u)] = (u32)g;
+    }
+}
+
+// the same two passes for one pair table of a GapSet: key = piece at g + oi | piece at g + oj
+__global__ void k2_gap_pass(LibView L, int pl, int oi, int oj, u32 npos, int pass, u32 *__restrict__ bucket, u32 *__restrict__ pos)
+{
+    const u32 pm = (1u << (2 * pl)) - 1u;
+    for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < (u64)npos; g += (u64)gridDim.x * blockDim.x) {
+        const u32 code = ((u32)lib_window64(L.seq, (u32)g + (u32)oi) & pm) | (((u32)lib_window64(L.seq, (u32)g + (u32)oj) & pm) << (2 * pl));
         if (pass == 0) atomicAdd(&bucket[code], 1u);
         else pos[atomicAdd(&bucket[code], 1u)] = (u32)g;
     }
@@ -167,44 +202,52 @@ struct K2Arrays {
     signed char *mm_of;
 };
 
-#define K2_HEAVY 16     // seed buckets at least this long are verified by the whole warp
-
-template <int W>
-__device__ __forceinline__ Query<W> query_bcast(const Query<W> &q, int src)
-{
-    Query<W> r;
-#pragma unroll
-    for (int w = 0; w < W; w++) {
-        r.s[w] = __shfl_sync(0xffffffffu, q.s[w], src);
-        r.n2[w] = __shfl_sync(0xffffffffu, q.n2[w], src);
-        r.len2[w] = __shfl_sync(0xffffffffu, q.len2[w], src);
-    }
-    r.n = __shfl_sync(0xffffffffu, q.n, src);
-    return r;
-}
-
 // One thread per still un-annotated unique sequence; a warp works through its 32
-// sequences seed by seed.  Short seed buckets are verified by the owning lane;
-// long ones (few-base seeds of the isomiR round, big libraries) are broadcast
-// and verified by all 32 lanes, then min-reduced back to the owner, so one
-// expensive sequence does not serialise its warp.  todo_in == nullptr means
+// sequences seed by seed.  When every lane has at most one candidate placement it
+// verifies its own; otherwise the candidate lists of the 32 lanes are laid end to
+// end and verified 32 at a time (k2_round.inc), so one sequence with a long list
+// (few-base seeds of the isomiR round, big libraries) does not serialise its warp.  todo_in == nullptr means
 // the identity list 0 .. *n_in-1.  Sequences that stay un-annotated (filtered
 // out by length, or without a valid placement) are appended to todo_out.
 // BAL (the multi-seed rounds on the miRNA library, whose seed tables have consecutive sizes): the seeds share the
 // region's spare bases, so the first ones are one base longer.  Those rounds work out of L1 and are issue
 // bound, so they are held to 8 CTAs per SM; the plain rounds wait on random library reads and keep the
 // compiler's natural register budget (a forced cap serialises the loads of a verification: +40 % time).
+// GAP: rounds whose library carries pair-of-pieces tables for their mismatch budget (GapSet above); queries whose
+// region a set serves take the m(m-1)/2 pair look-ups instead of the e + 1 classic seeds.
 #define K2_ROUND_NAME k2_round
 #define K2_LAUNCH_BOUNDS __launch_bounds__(128)
 #define K2_BAL 0
+#define K2_GAP 0
 #include "k2_round.inc"
 #undef K2_ROUND_NAME
 #undef K2_LAUNCH_BOUNDS
 #undef K2_BAL
+#undef K2_GAP
 #define K2_ROUND_NAME k2_round_balanced
 #define K2_LAUNCH_BOUNDS __launch_bounds__(128, 8)
 #define K2_BAL 1
+#define K2_GAP 0
 #include "k2_round.inc"
 #undef K2_ROUND_NAME
 #undef K2_LAUNCH_BOUNDS
 #undef K2_BAL
+#undef K2_GAP
+#define K2_ROUND_NAME k2_round_pairs
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128)
+#define K2_BAL 1
+#define K2_GAP 1
+#include "k2_round.inc"
+#undef K2_ROUND_NAME
+#undef K2_LAUNCH_BOUNDS
+#undef K2_BAL
+#undef K2_GAP
+#define K2_ROUND_NAME k2_round_pairs8
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, 8)
+#define K2_BAL 1
+#define K2_GAP 1
+#include "k2_round.inc"
+#undef K2_ROUND_NAME
+#undef K2_LAUNCH_BOUNDS
+#undef K2_BAL
+#undef K2_GAP

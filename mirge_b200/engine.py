@@ -118,6 +118,11 @@ class Engine:
         self._ck(lib.mirge_set_option(self.h, 1, int(on)))
 
     # -- genome passes ------------------------------------------------------------
+
+    def pair_seeds(self, threshold=16):
+        """MIRGE_OPT_PAIR_SEEDS: pair-of-pieces seed tables for short queries wherever the plain seeds would offer at
+        least `threshold` candidates per query (1 = wherever possible, 0 = never).  Set before loading libraries."""
+        self._ck(lib.mirge_set_option(self.h, 2, int(threshold)))
     def load_genome(self, names, seqs):
         """index.Libs/<sp>_genome (library slot 8)."""
         off = np.zeros(len(seqs) + 1, np.uint64)

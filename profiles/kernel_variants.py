@@ -2,9 +2,11 @@
 the 25 M-read workload is generated once (about 8 s), every variant then costs three feeds.
 
     gpurun -- python profiles/kernel_variants.py 25000000 0,0x100,0x200 0
-        argv[1] reads, argv[2] K1 modes, argv[3] K2 modes (optional; loads the libraries)
+        argv[1] reads, argv[2] K1 modes, argv[3] K2 modes (optional; loads the libraries), argv[4] exchange kernels (0/1),
+        argv[5] pair-seed thresholds to run the K2 modes under (MIRGE_OPT_PAIR_SEEDS; default: the library default)
     mode bits: 1 all-column search for every read, 2 literal DP, 4 prefilter off, 0x100 no count updates (diagnostic),
-    0x200 classification only (diagnostic), 0x800 count cache off, 0x1000 chunked K2 to-do appends
+    0x200 classification only (diagnostic), 0x800 count cache off, 0x1000 chunked K2 to-do appends,
+    0x4000 pair-seed rounds swap their register budget (8 CTAs/SM <-> natural)
 Diagnostic modes give wrong tables on purpose; they only attribute time."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -35,10 +37,14 @@ for mode in modes:
 K2MODES = [int(x, 0) for x in sys.argv[3].split(",") if x] if len(sys.argv) > 3 else []
 # K2 variants (needs libraries)
 from mirge_b200.engine import LIB_IDS
-if K2MODES:
-    for t, i in LIB_IDS.items():
-        eng.load_library(i, *world.libs[t])
-for mode in K2MODES:
+PAIRS = [int(x) for x in sys.argv[5].split(",") if x] if len(sys.argv) > 5 else [None]
+for ps, mode in [(a, b) for a in (PAIRS if K2MODES else []) for b in K2MODES]:
+    if mode == K2MODES[0]:
+        if ps is not None:
+            eng.pair_seeds(ps)
+        for t, i in LIB_IDS.items():
+            eng.load_library(i, *world.libs[t])
+        print('pair_seeds', ps, flush=True)
     eng.set_trim_mode(mode)
     for it in range(3):
         eng.reset()
