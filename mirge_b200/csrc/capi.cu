@@ -89,7 +89,8 @@ struct mirge_ctx {
     // mapping
     DevLib libs[MIRGE_N_LIBS];
     u32 *d_todo[2] = {nullptr, nullptr};
-    u64 *d_todo_n = nullptr;        // [MIRGE_N_ROUNDS + 1]
+    u32 *d_todo_long = nullptr;     // ids that skip round 0's length filter (k2_fill_range)
+    u64 *d_todo_n = nullptr;        // [MIRGE_N_ROUNDS + 2]
     u64 *d_round_stats = nullptr;   // [2][MIRGE_N_ROUNDS]
     bool annotated = false;
     bool annotate_while_feeding = false;
@@ -292,9 +293,11 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_ctr, (6 + 2 * (size_t)n_samples) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_len_hist, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64)));
     // to-do lists: every unique once, plus the partly used chunk of every appending warp
-    CK(cudaMalloc(&ctx->d_todo[0], (max_unique + (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
-    CK(cudaMalloc(&ctx->d_todo[1], (max_unique + (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
-    CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 1) * sizeof(u64)));
+    // slack: the chunked appends pad every warp's last chunk, and two kernels (rounds 0 and 1) append to one list
+    CK(cudaMalloc(&ctx->d_todo[0], (max_unique + 2 * (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo[1], (max_unique + 2 * (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo_long, max_unique * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 2) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_k0state, sizeof(K0State)));
     CK(cudaMalloc(&ctx->d_qn, 4 * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_round_stats, 2 * MIRGE_N_ROUNDS * sizeof(u64)));
@@ -331,7 +334,7 @@ void mirge_destroy(mirge_ctx *ctx)
     cudaFree(ctx->d_slots); cudaFree(ctx->d_useq); cudaFree(ctx->d_unmask); cudaFree(ctx->d_ulen); cudaFree(ctx->d_counts);
     cudaFree(ctx->d_round_of); cudaFree(ctx->d_mm_of); cudaFree(ctx->d_ref_of); cudaFree(ctx->d_pos_of);
     cudaFree(ctx->d_ctr); cudaFree(ctx->d_len_hist); cudaFree(ctx->d_todo[0]); cudaFree(ctx->d_todo[1]);
-    cudaFree(ctx->d_todo_n); cudaFree(ctx->d_round_stats); cudaFree(ctx->d_annot);
+    cudaFree(ctx->d_todo_long); cudaFree(ctx->d_todo_n); cudaFree(ctx->d_round_stats); cudaFree(ctx->d_annot);
     cudaFree(ctx->d_mir_quant); cudaFree(ctx->d_mir_iscan); cudaFree(ctx->d_lib_totals); cudaFree(ctx->d_tally);
     for (auto e : ctx->copy_events) cudaEventDestroy(e);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -880,12 +883,27 @@ __global__ void k2_take_range(const u64 *n_unique, u64 max_unique, u64 *annot)
     annot[1] = lo; annot[2] = hi - lo; annot[0] = hi;
 }
 
-// the first round's to-do list: the claimed id range written out (the round kernels keep their register budget: one
-// more kernel argument cost k2_round eight registers and an eighth of its occupancy)
-__global__ void k2_fill_range(const u64 *annot, u32 *todo)
+// The first to-do lists: the claimed id range written out (the round kernels keep their register budget: one more
+// kernel argument cost k2_round eight registers and an eighth of its occupancy).  Rounds 0 and 1 filter by length
+// on complementary conditions (len < 26: miRNA, len > 25: hairpin), so the range is dealt into two lists here and each
+// of the two rounds only ever sees the sequences it would search; both append their misses to round 2's list.
+// split_len == 0: one list (todo_a).
+__global__ void k2_fill_range(const u64 *annot, const u8 *__restrict__ ulen, int split_len, u32 *todo_a, u64 *n_a, u32 *todo_b, u64 *n_b)
 {
     const u64 base = annot[1], n = annot[2];
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) todo[i] = (u32)(base + i);
+    const unsigned lane = threadIdx.x & 31;
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x; i0 < n; i0 += (u64)gridDim.x * blockDim.x) {
+        const u64 i = i0 + threadIdx.x;
+        const bool in = i < n;
+        const bool to_b = in && split_len > 0 && (int)ulen[base + i] >= split_len;
+        const unsigned ba = __ballot_sync(0xffffffffu, in && !to_b), bb = __ballot_sync(0xffffffffu, to_b);
+        u64 sa = 0, sb = 0;
+        if (lane == 0) { if (ba) sa = atomicAdd(n_a, (u64)__popc(ba)); if (bb) sb = atomicAdd(n_b, (u64)__popc(bb)); }
+        sa = __shfl_sync(0xffffffffu, sa, 0); sb = __shfl_sync(0xffffffffu, sb, 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (to_b) todo_b[sb + __popc(bb & below)] = (u32)(base + i);
+        else if (in) todo_a[sa + __popc(ba & below)] = (u32)(base + i);
+    }
 }
 
 static int annot_clear(mirge_ctx *ctx)
@@ -904,9 +922,13 @@ template <int W>
 static int annotate_impl(mirge_ctx *ctx)
 {
     cudaStream_t st = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 1) * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 2) * sizeof(u64), st));
     k2_take_range<<<1, 1, 0, st>>>(ctx->d_ctr, ctx->max_unique, ctx->d_annot);
-    k2_fill_range<<<148 * 4, 256, 0, st>>>(ctx->d_annot, ctx->d_todo[1]);
+    // rounds 0 and 1 on complementary length classes: each gets its own list, both feed round 2's (d_todo[1], d_todo_n[2])
+    const bool split = ROUNDS[0].len_filter < 0 && ROUNDS[1].len_filter == -ROUNDS[0].len_filter - 1;
+    u64 *n_long = ctx->d_todo_n + MIRGE_N_ROUNDS + 1;
+    k2_fill_range<<<148 * 4, 256, 0, st>>>(ctx->d_annot, ctx->d_ulen, split ? -ROUNDS[0].len_filter : 0,
+                                           split ? ctx->d_todo[0] : ctx->d_todo[1], ctx->d_todo_n, ctx->d_todo_long, n_long);
     ctx->n_launches += 2;
     K2Arrays A;
     A.useq = ctx->d_useq; A.unmask = ctx->d_unmask; A.ulen = ctx->d_ulen;
@@ -921,23 +943,29 @@ static int annotate_impl(mirge_ctx *ctx)
         R.round = r; R.len_filter = rs.len_filter; R.mode = rs.mode; R.param = rs.param; R.trim5 = rs.trim5; R.trim3 = rs.trim3;
         R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs; R.chunked = (ctx->force_slow & 0x1000) ? 1 : 0;   // per-tile appends measured faster for the heavy rounds
         for (int t = 0; t < l.ntabs; t++) { R.tabs[t].k = l.tab_k[t]; R.tabs[t].bucket_off = l.tab_off[t]; R.tabs[t].pos = l.tab_pos[t]; }
+        R.kcons = l.ntabs > 0;
+        for (int t = 1; t < l.ntabs; t++) if (l.tab_k[t] != l.tab_k[t - 1] + 1) R.kcons = 0;
         for (int g = 0; g < l.ngap; g++)
             if (rs.param >= 1 && l.gap[g].m == rs.param + 2 && R.ngap < K2_MAX_GAPSETS) { R.gap[R.ngap++] = l.gap[g]; R.gap_pairs = l.gap[g].m * (l.gap[g].m - 1) / 2; }
         const u32 *todo_in = ctx->d_todo[(r + 1) & 1];             // round 0 reads the range list in d_todo[1]
-        const u64 *n_in = r == 0 ? ctx->d_annot + 2 : ctx->d_todo_n + r;
+        const u64 *n_in = ctx->d_todo_n + r;
+        u32 *todo_out = ctx->d_todo[r & 1];
+        u64 *n_out = ctx->d_todo_n + r + 1;
+        if (split && r == 0) { todo_in = ctx->d_todo[0]; todo_out = ctx->d_todo[1]; n_out = ctx->d_todo_n + 2; }
+        if (split && r == 1) { todo_in = ctx->d_todo_long; n_in = n_long; }
         ProfScope ps(ctx, KID_K2_ROUND0 + r);
         const bool eight = !(ctx->force_slow & 0x4000);    // 8 CTAs/SM measured faster for both pair rounds (0.57 vs 0.94 ms, 0.81 vs 1.19 ms)
         if (R.ngap > 0 && eight)                            // short queries go through the pair-of-pieces tables
-            k2_round_pairs8<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+            k2_round_pairs8<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else if (R.ngap > 0)
-            k2_round_pairs<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+            k2_round_pairs<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else if (rs.param > 0 && rs.lib == MIRGE_LIB_MIRNA) // several seeds over consecutive table sizes: balance them
-            k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+            k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else
-            k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, ctx->d_todo[r & 1], ctx->d_todo_n + r + 1, L, R,
+            k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                        ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
     }
     CK(cudaGetLastError());

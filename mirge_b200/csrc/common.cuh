@@ -136,6 +136,17 @@ template <int W>
 __device__ __forceinline__ void pseq_shift(PSeq<W> &p, int b)
 {
     if (b <= 0) return;
+    if constexpr (W == 2) {
+        // two words: plain selects (the generic compare-select chains below are turned into indexed local-memory
+        // accesses by the compiler, which parks the whole sequence on the stack)
+        const bool up = b >= 32;
+        const int bs = (b & 31) * 2;
+        const u64 lo = up ? p.s[1] : p.s[0], hi = up ? 0ull : p.s[1];
+        p.s[0] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+        p.s[1] = up ? 0ull : (hi >> bs);
+        p.nm[0] = b >= 64 ? 0ull : (p.nm[0] >> b);
+        return;
+    }
     {
         int ws = b >> 5, bs = (b & 31) * 2;
         u64 t[W];
@@ -219,6 +230,11 @@ template <int W>
 __host__ __device__ __forceinline__ u64 words_window64(const u64 *a, int so)
 {
     const int ws = so >> 5, bs = (so & 31) * 2;
+    if constexpr (W == 2) {     // plain selects keep the words in registers (see pseq_shift)
+        const u64 a0 = a[0], a1 = a[1];
+        const u64 lo2 = ws == 0 ? a0 : (ws == 1 ? a1 : 0ull), hi2 = ws == 0 ? a1 : 0ull;
+        return bs ? ((lo2 >> bs) | (hi2 << (64 - bs))) : lo2;
+    }
     u64 lo = 0ull, hi = 0ull;
 #pragma unroll
     for (int w = 0; w < W; w++) {

@@ -64,6 +64,7 @@ struct RoundParams {
     int highest;        // keep the highest (ref, pos) of the best stratum
     int polyT;          // pre-tRNA round: strip trailing T{3,}, remainder >= 11 (:664-686)
     int ntabs;
+    int kcons;          // tabs[] hold consecutive seed lengths (the table for a length is found by subtraction)
     int chunked;        // to-do appends: 1 = chunk reservation per warp (lists hold padding), 0 = one atomic per warp and tile
     KmerTab tabs[K2_MAX_TABS];   // ascending k
     int ngap, gap_pairs;         // pair-of-pieces sets for this round's mismatch budget, pairs per set
