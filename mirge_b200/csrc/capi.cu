@@ -89,8 +89,8 @@ struct mirge_ctx {
     // mapping
     DevLib libs[MIRGE_N_LIBS];
     u32 *d_todo[2] = {nullptr, nullptr};
-    u32 *d_todo_long = nullptr;     // ids that skip round 0's length filter (k2_fill_range)
-    u64 *d_todo_n = nullptr;        // [MIRGE_N_ROUNDS + 2]
+    u32 *d_todo_long = nullptr;     // third list: ids that skip round 0's length filter (k2_fill_range), later the list past the poly-T round
+    u64 *d_todo_n = nullptr;        // [MIRGE_N_ROUNDS + 3]
     u64 *d_round_stats = nullptr;   // [2][MIRGE_N_ROUNDS]
     bool annotated = false;
     bool annotate_while_feeding = false;
@@ -293,11 +293,10 @@ int mirge_create(int device, int n_samples, int spike_in, uint64_t max_unique, i
     CK(cudaMalloc(&ctx->d_ctr, (6 + 2 * (size_t)n_samples) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_len_hist, (size_t)(ctx->max_len + 1) * n_samples * sizeof(u64)));
     // to-do lists: every unique once, plus the partly used chunk of every appending warp
-    // slack: the chunked appends pad every warp's last chunk, and two kernels (rounds 0 and 1) append to one list
-    CK(cudaMalloc(&ctx->d_todo[0], (max_unique + 2 * (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
-    CK(cudaMalloc(&ctx->d_todo[1], (max_unique + 2 * (size_t)WARPQ_CHUNK * ctx->max_warps) * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo[0], max_unique * sizeof(u32)));
+    CK(cudaMalloc(&ctx->d_todo[1], max_unique * sizeof(u32)));
     CK(cudaMalloc(&ctx->d_todo_long, max_unique * sizeof(u32)));
-    CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 2) * sizeof(u64)));
+    CK(cudaMalloc(&ctx->d_todo_n, (MIRGE_N_ROUNDS + 3) * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_k0state, sizeof(K0State)));
     CK(cudaMalloc(&ctx->d_qn, 4 * sizeof(u64)));
     CK(cudaMalloc(&ctx->d_round_stats, 2 * MIRGE_N_ROUNDS * sizeof(u64)));
@@ -922,11 +921,11 @@ template <int W>
 static int annotate_impl(mirge_ctx *ctx)
 {
     cudaStream_t st = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 2) * sizeof(u64), st));
+    CK(cudaMemsetAsync(ctx->d_todo_n, 0, (MIRGE_N_ROUNDS + 3) * sizeof(u64), st));
     k2_take_range<<<1, 1, 0, st>>>(ctx->d_ctr, ctx->max_unique, ctx->d_annot);
     // rounds 0 and 1 on complementary length classes: each gets its own list, both feed round 2's (d_todo[1], d_todo_n[2])
     const bool split = ROUNDS[0].len_filter < 0 && ROUNDS[1].len_filter == -ROUNDS[0].len_filter - 1;
-    u64 *n_long = ctx->d_todo_n + MIRGE_N_ROUNDS + 1;
+    u64 *n_long = ctx->d_todo_n + MIRGE_N_ROUNDS + 1, *n_past = ctx->d_todo_n + MIRGE_N_ROUNDS + 2;
     k2_fill_range<<<148 * 4, 256, 0, st>>>(ctx->d_annot, ctx->d_ulen, split ? -ROUNDS[0].len_filter : 0,
                                            split ? ctx->d_todo[0] : ctx->d_todo[1], ctx->d_todo_n, ctx->d_todo_long, n_long);
     ctx->n_launches += 2;
@@ -941,7 +940,7 @@ static int annotate_impl(mirge_ctx *ctx)
         RoundParams R;
         memset(&R, 0, sizeof R);
         R.round = r; R.len_filter = rs.len_filter; R.mode = rs.mode; R.param = rs.param; R.trim5 = rs.trim5; R.trim3 = rs.trim3;
-        R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs; R.chunked = (ctx->force_slow & 0x1000) ? 1 : 0;   // per-tile appends measured faster for the heavy rounds
+        R.highest = rs.highest; R.polyT = rs.polyT; R.ntabs = l.ntabs;
         for (int t = 0; t < l.ntabs; t++) { R.tabs[t].k = l.tab_k[t]; R.tabs[t].bucket_off = l.tab_off[t]; R.tabs[t].pos = l.tab_pos[t]; }
         R.kcons = l.ntabs > 0;
         for (int t = 1; t < l.ntabs; t++) if (l.tab_k[t] != l.tab_k[t - 1] + 1) R.kcons = 0;
@@ -953,6 +952,12 @@ static int annotate_impl(mirge_ctx *ctx)
         u64 *n_out = ctx->d_todo_n + r + 1;
         if (split && r == 0) { todo_in = ctx->d_todo[0]; todo_out = ctx->d_todo[1]; n_out = ctx->d_todo_n + 2; }
         if (split && r == 1) { todo_in = ctx->d_todo_long; n_in = n_long; }
+        // the poly-T round only takes sequences ending in TTT: the round before it sends the others straight to the list
+        // of the round after it (the third buffer, free again by then), where the poly-T round appends its own misses
+        const bool tail_skip = !(ctx->force_slow & 0x1000);
+        if (tail_skip && r + 2 < nrounds && ROUNDS[r + 1].polyT && r >= 2) { R.next_tail3T = 1; R.bypass_out = ctx->d_todo_long; R.bypass_n = n_past; }
+        if (tail_skip && r >= 3 && rs.polyT && r + 1 < nrounds) { todo_out = ctx->d_todo_long; n_out = n_past; }
+        if (tail_skip && r >= 4 && ROUNDS[r - 1].polyT) { todo_in = ctx->d_todo_long; n_in = n_past; }
         ProfScope ps(ctx, KID_K2_ROUND0 + r);
         const bool eight = !(ctx->force_slow & 0x4000);    // 8 CTAs/SM measured faster for both pair rounds (0.57 vs 0.94 ms, 0.81 vs 1.19 ms)
         if (R.ngap > 0 && eight)                            // short queries go through the pair-of-pieces tables

@@ -65,7 +65,9 @@ struct RoundParams {
     int polyT;          // pre-tRNA round: strip trailing T{3,}, remainder >= 11 (:664-686)
     int ntabs;
     int kcons;          // tabs[] hold consecutive seed lengths (the table for a length is found by subtraction)
-    int chunked;        // to-do appends: 1 = chunk reservation per warp (lists hold padding), 0 = one atomic per warp and tile
+    int next_tail3T;    // the NEXT round is the poly-T round: misses that do not end in TTT go to bypass_out instead
+    u32 *bypass_out;    // ... the list the round after the next reads (the next round appends its own misses there)
+    u64 *bypass_n;
     KmerTab tabs[K2_MAX_TABS];   // ascending k
     int ngap, gap_pairs;         // pair-of-pieces sets for this round's mismatch budget, pairs per set
     GapSet gap[K2_MAX_GAPSETS];
@@ -203,6 +205,19 @@ struct K2Arrays {
     signed char *mm_of;
 };
 
+// per-warp output buffer of the round kernels (ids) and its flush: one reservation on the list counter, coalesced copy
+#define K2_OB 128
+__device__ __forceinline__ void k2_flush(const u32 *buf, u32 n, u32 *__restrict__ out, u64 *__restrict__ counter)
+{
+    const unsigned lane = threadIdx.x & 31;
+    __syncwarp();
+    u64 b = 0;
+    if (lane == 0) b = atomicAdd(counter, (u64)n);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    for (u32 x = lane; x < n; x += 32) out[b + x] = buf[x];
+    __syncwarp();
+}
+
 // One thread per still un-annotated unique sequence; a warp works through its 32
 // sequences seed by seed.  When every lane has at most one candidate placement it
 // verifies its own; otherwise the candidate lists of the 32 lanes are laid end to
@@ -217,7 +232,7 @@ struct K2Arrays {
 // GAP: rounds whose library carries pair-of-pieces tables for their mismatch budget (GapSet above); queries whose
 // region a set serves take the m(m-1)/2 pair look-ups instead of the e + 1 classic seeds.
 #define K2_ROUND_NAME k2_round
-#define K2_LAUNCH_BOUNDS __launch_bounds__(128)
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, 8)
 #define K2_BAL 0
 #define K2_GAP 0
 #include "k2_round.inc"

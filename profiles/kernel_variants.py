@@ -5,7 +5,7 @@ the 25 M-read workload is generated once (about 8 s), every variant then costs t
         argv[1] reads, argv[2] K1 modes, argv[3] K2 modes (optional; loads the libraries), argv[4] exchange kernels (0/1),
         argv[5] pair-seed thresholds to run the K2 modes under (MIRGE_OPT_PAIR_SEEDS; default: the library default)
     mode bits: 1 all-column search for every read, 2 literal DP, 4 prefilter off, 0x100 no count updates (diagnostic),
-    0x200 classification only (diagnostic), 0x800 count cache off, 0x1000 chunked K2 to-do appends,
+    0x200 classification only (diagnostic), 0x800 count cache off,
     0x4000 pair-seed rounds swap their register budget (8 CTAs/SM <-> natural)
 Diagnostic modes give wrong tables on purpose; they only attribute time."""
 import sys, os, json
