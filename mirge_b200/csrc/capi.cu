@@ -961,16 +961,16 @@ static int annotate_impl(mirge_ctx *ctx)
         ProfScope ps(ctx, KID_K2_ROUND0 + r);
         const bool eight = !(ctx->force_slow & 0x4000);    // 8 CTAs/SM measured faster for both pair rounds (0.57 vs 0.94 ms, 0.81 vs 1.19 ms)
         if (R.ngap > 0 && eight)                            // short queries go through the pair-of-pieces tables
-            k2_round_pairs8<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
+            k2_round_pairs8<W><<<148 * K2_CTAS, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else if (R.ngap > 0)
-            k2_round_pairs<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
+            k2_round_pairs<W><<<148 * K2_CTAS, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else if (rs.param > 0 && rs.lib == MIRGE_LIB_MIRNA) // several seeds over consecutive table sizes: balance them
-            k2_round_balanced<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
+            k2_round_balanced<W><<<148 * K2_CTAS, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else
-            k2_round<W><<<148 * 8, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
+            k2_round<W><<<148 * K2_CTAS, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                        ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
     }
     CK(cudaGetLastError());

@@ -15,6 +15,9 @@
 #include "common.cuh"
 
 #define K2_MAX_TABS 6
+#ifndef K2_CTAS
+#define K2_CTAS 8       // resident CTAs per SM of the round kernels (64 registers); the grid is one wave of them
+#endif
 
 struct LibView {
     const u64 *seq;        // 2-bit packed concatenation (zero padded by >= 5 words)
@@ -232,7 +235,7 @@ __device__ __forceinline__ void k2_flush(const u32 *buf, u32 n, u32 *__restrict_
 // GAP: rounds whose library carries pair-of-pieces tables for their mismatch budget (GapSet above); queries whose
 // region a set serves take the m(m-1)/2 pair look-ups instead of the e + 1 classic seeds.
 #define K2_ROUND_NAME k2_round
-#define K2_LAUNCH_BOUNDS __launch_bounds__(128, 8)
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, K2_CTAS)
 #define K2_BAL 0
 #define K2_GAP 0
 #include "k2_round.inc"
@@ -241,7 +244,7 @@ __device__ __forceinline__ void k2_flush(const u32 *buf, u32 n, u32 *__restrict_
 #undef K2_BAL
 #undef K2_GAP
 #define K2_ROUND_NAME k2_round_balanced
-#define K2_LAUNCH_BOUNDS __launch_bounds__(128, 8)
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, K2_CTAS)
 #define K2_BAL 1
 #define K2_GAP 0
 #include "k2_round.inc"
@@ -259,7 +262,7 @@ __device__ __forceinline__ void k2_flush(const u32 *buf, u32 n, u32 *__restrict_
 #undef K2_BAL
 #undef K2_GAP
 #define K2_ROUND_NAME k2_round_pairs8
-#define K2_LAUNCH_BOUNDS __launch_bounds__(128, 8)
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, K2_CTAS)
 #define K2_BAL 1
 #define K2_GAP 1
 #include "k2_round.inc"
