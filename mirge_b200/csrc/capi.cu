@@ -244,6 +244,8 @@ static void k1pre_build(const TrimParams &tp, const K1Thr &thr, K1Pre &pre)
         }
     }
     pre.m = m; pre.icap = icap;
+    pre.np = K; pre.np_inv = (65536 + K - 1) / K;                       // pigeonhole pieces of the class-1 filter (k1_piece_hit_warp)
+    for (int q = 0; q <= K; q++) pre.pb[q] = (u8)((q * m) / K);
     pre.anchor_rep = (u32)(tp.aw[0][0] & 0xFFull) * 0x01010101u;
     pre.enabled = 1;
 }

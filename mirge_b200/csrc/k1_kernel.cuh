@@ -536,6 +536,7 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
     __shared__ u32 sh_cid[K1_CC * (K1A_THREADS / 32)], sh_ccnt[K1_CC * (K1A_THREADS / 32)];
     __shared__ K1Pre pre;
     __shared__ u64 sh_bm[4 * (W / 2) * K1A_THREADS];     // base-position masks of the pigeonhole filter
+    __shared__ u8 sh_c1lane[K1A_THREADS], sh_c1lim[K1A_THREADS];
     for (int b = threadIdx.x; b < K1_HIST(W); b += K1A_THREADS) sh_hist[b] = 0;
     for (int b = threadIdx.x; b < K1_CC * (K1A_THREADS / 32); b += K1A_THREADS) { sh_cid[b] = 0xFFFFFFFFu; sh_ccnt[b] = 0; }
     u32 *wh = sh_hist;
@@ -547,7 +548,6 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
     const bool use_pre = pre.enabled && !(force_slow & 4);
     const int mode = tp_param.mode, uncond = tp_param.uncond, min_length = tp_param.min_length;
     const u64 aw0 = tp_param.aw[0][0];
-    const int m0 = tp_param.alen[0], kmax0 = m0 <= MIRGE_MAX_ADAPTER_LEN ? thr_param.v[m0] : -1;
     K1QRec<W> *q2 = reinterpret_cast<K1QRec<W> *>(Q.q2), *q3 = reinterpret_cast<K1QRec<W> *>(Q.q3);
     u32 my_kept = 0, my_c1 = 0;
     WarpQ wq2 = {0, 0}, wq3 = {0, 0};
@@ -573,9 +573,11 @@ k1_trim_collapse(const u64 *__restrict__ bases, const u64 *__restrict__ nmask, c
             else cls = 2;
         }
         if (!live) cls = -1;
-        if (cls == 1) {
-            my_c1++;
-            cls = k1_piece_hit<W>(p, lim, m0, kmax0, aw0, sh_bm + threadIdx.x, K1A_THREADS) ? 2 : 0;
+        const unsigned c1m = __ballot_sync(0xffffffffu, cls == 1);
+        if (c1m) {                                                         // the warp's class-1 reads, piece by piece (warp-collective)
+            const bool mine = cls == 1;
+            const bool hit = k1_piece_hit_warp<W>(p, mine, c1m, lim, pre, aw0, sh_bm, K1A_THREADS, sh_c1lane, sh_c1lim);
+            if (mine) { my_c1++; cls = hit ? 2 : 0; }
         }
         k1q_push<W>(cls == 2, Q.n + 0, q2, wq2, p, n);
         k1q_push<W>(cls == 3, Q.n + 1, q3, wq3, p, n);

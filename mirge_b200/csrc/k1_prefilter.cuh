@@ -45,6 +45,8 @@ struct K1Pre {
     u32 safe_p;
     u32 safe_len[K1PRE_MAXI + 1];
     u8 fullreach[32];
+    int np, np_inv;                   // class-1 piece filter: thr[m] + 1 pieces; ceil(65536 / np) (task index -> read, piece)
+    u8 pb[36];                        // piece q covers adapter bases pb[q] .. pb[q + 1] - 1
 };
 
 // Returns the class (0, 1, 2).  Class 0/1: rstart = start of FULL / E.  Class 1: limit =
@@ -226,6 +228,87 @@ __host__ __device__ __forceinline__ bool k1_piece_hit(const PSeq<W> &p, int limi
     }
     return hit;
 }
+
+#ifdef __CUDACC__
+// The same filter for all class-1 reads of a warp at once.  Only about a quarter of the reads are class 1, so run lane
+// by lane the filter kept three lanes in four idle for a third of the kernel's instructions; here every (read, piece)
+// pair is one work item, dealt out over the 32 lanes.  Owners publish their position masks (bm, layout
+// [(x * NP + w) * stride + thread]) and their column limit in shared memory; a work item reads its owner's.
+// c1m = ballot of the class-1 lanes; lane_list / lim_list: per-thread shared scratch.  Warp-collective.
+template <int W>
+__device__ __forceinline__ bool k1_piece_hit_warp(const PSeq<W> &p, bool mine, unsigned c1m, int limit, const K1Pre &pre, u64 aw,
+                                                  u64 *bm, int stride, u8 *lane_list, u8 *lim_list)
+{
+    constexpr int NP = W / 2;
+    const unsigned lane = threadIdx.x & 31, wbase = threadIdx.x & ~31u;
+    const int rank = __popc(c1m & ((1u << lane) - 1u));
+    if (mine) {
+        u64 *o = bm + threadIdx.x;
+#pragma unroll
+        for (int w = 0; w < NP; w++) {
+            const u32 d0 = deinterleave32((u32)p.s[2 * w]), d1 = deinterleave32((u32)(p.s[2 * w] >> 32));
+            const u32 d2 = deinterleave32((u32)p.s[2 * w + 1]), d3 = deinterleave32((u32)(p.s[2 * w + 1] >> 32));
+            const u64 L = (u64)((d0 & 0xFFFFu) | (d1 << 16)) | ((u64)((d2 & 0xFFFFu) | (d3 << 16)) << 32);
+            const u64 H = (u64)((d0 >> 16) | (d1 & 0xFFFF0000u)) | ((u64)((d2 >> 16) | (d3 & 0xFFFF0000u)) << 32);
+            o[(0 * NP + w) * stride] = ~(L | H);
+            o[(1 * NP + w) * stride] = L & ~H;
+            o[(2 * NP + w) * stride] = H & ~L;
+            o[(3 * NP + w) * stride] = L & H;
+        }
+        lane_list[wbase + rank] = (u8)lane;
+        lim_list[threadIdx.x] = (u8)limit;                     // limit <= read length <= 128
+    }
+    __syncwarp();
+    const int np = pre.np, ntask = __popc(c1m) * np;
+    bool myhit = false;
+    for (int t0 = 0; t0 < ntask; t0 += 32) {
+        const int t = t0 + (int)lane;
+        bool h = false;
+        if (t < ntask) {
+            const int k = (t * pre.np_inv) >> 16, q = t - k * np;      // exact for t < 32 * 33
+            const int ot = (int)wbase + lane_list[wbase + k];
+            const int b0 = pre.pb[q], b1 = pre.pb[q + 1], len = b1 - b0;
+            const int cnt = (int)lim_list[ot] - len + 1;             // start positions 0 .. limit - len
+            if (cnt > 0 && len > 0) {
+                const u64 *o = bm + ot;
+                u64 acc[NP];
+                {
+                    const int c = (int)((aw >> (2 * (b1 - 1))) & 3ull);
+#pragma unroll
+                    for (int w = 0; w < NP; w++) acc[w] = o[(c * NP + w) * stride];
+                }
+                for (int tt = b1 - 2; tt >= b0; tt--) {
+                    const int c = (int)((aw >> (2 * tt)) & 3ull);
+#pragma unroll
+                    for (int w = 0; w < NP; w++) {
+                        const u64 up = (w + 1 < NP) ? acc[w + 1] << 63 : 0ull;
+                        acc[w] = o[(c * NP + w) * stride] & ((acc[w] >> 1) | up);
+                    }
+                }
+                u64 any = 0;
+#pragma unroll
+                for (int w = 0; w < NP; w++) {
+                    const int lo = 64 * w;
+                    const u64 pm = (cnt <= lo) ? 0ull : (cnt >= lo + 64) ? ~0ull : ((1ull << (cnt - lo)) - 1ull);
+                    any |= acc[w] & pm;
+                }
+                h = any != 0ull;
+            }
+        }
+        const unsigned hb = __ballot_sync(0xffffffffu, h);
+        if (mine) {                                            // my items are bits rank * np - t0 .. + np of this pass
+            const int lo = rank * np - t0;
+            const int a = lo < 0 ? 0 : lo, b = lo + np > 32 ? 32 : lo + np;
+            if (a < b) {
+                const unsigned rm = ((b - a) >= 32 ? 0xffffffffu : ((1u << (b - a)) - 1u)) << a;
+                if (hb & rm) myhit = true;
+            }
+        }
+    }
+    __syncwarp();                                              // the scratch is rewritten by the warp's next tile
+    return myhit;
+}
+#endif
 
 // Class "1b" (NOT wired into the kernels yet; exercised on the host by tests/test_k1_host_compiled.py): reads that
 // end with an exact adapter prefix of l bases (l >= min_overlap) which the tables cannot settle -- typically a SHORT

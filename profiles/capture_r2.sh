@@ -13,6 +13,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:'k0_parse_spec|k1_trim_collapse|k1_general_search|k1_slow_search' -s 4 -c 4 -o gpurun_out/r2_k0k1 -f python profiles/kernel_variants.py 25000000 0 > gpurun_out/r2_k0k1_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k2_round' -s 9 -c 9 -o gpurun_out/r2_k2 -f python profiles/kernel_variants.py 25000000 "" 0 > gpurun_out/r2_k2_ncu.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+# 3b. DRAM bytes per family from those captures: bench.py reports them as roofline.traffic
+python profiles/make_traffic.py gpurun_out/r2_k0k1.ncu-rep gpurun_out/r2_k2.ncu-rep && cp profiles/r2_traffic.json gpurun_out/r2_traffic.json
 # 4. the bench line itself (not under a profiler)
 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>> gpurun_out/r2_bench_final.err

@@ -42,6 +42,10 @@ def main():
     # a report may hold several launches: keep the N-th one (env LAUNCH, default 0)
     starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
     which = int(os.environ.get('LAUNCH', '0'))
+    # ncu prints every launch twice (two views of the same SASS): step over the duplicates
+    heads = starts[:-1]
+    if len(heads) % 2 == 0 and all(rows[heads[k]][1] == rows[heads[k + 1]][1] for k in range(0, len(heads), 2)):
+        which *= 2
     rows = rows[starts[which]:starts[which + 1]]
     hdr, data = rows[1], rows[2:]
     iA, iE, iS, iT = hdr.index('Address'), hdr.index('Instructions Executed'), hdr.index('# Samples'), hdr.index('Thread Instructions Executed')
