@@ -203,6 +203,7 @@ int mirge_profile_read(mirge_ctx *ctx, double *ms, uint64_t *launches, const cha
  * bit-vector search), 3 through the literal banded cutadapt DP, 4 switches the
  * exact-match prefilter off (every read takes the windowed bit-vector search),
  * 0x2000 parses FASTQ with the exact chained-scan kernel only (no speculation),
+ * 0x1000 routes every miss through the poly-T round (no bypass list),
  * 0 restores the default, -1 leaves the setting unchanged; slow_reads (may be
  * NULL) receives the number of reads that went through the slow queue so far.
  * Results are identical in every mode. */

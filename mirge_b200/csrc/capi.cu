@@ -615,6 +615,7 @@ static int build_gap_set(mirge_ctx *ctx, DevLib &l, const LibView &L, int m, int
     cudaFree(cursor); cudaFree(scratch);
     if (e != cudaSuccess) {
         cudaFree(off); cudaFree(pos);
+        if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return MIRGE_OK; }   // no room: the plain seeds serve every query
         ctx->err = std::string("pair seed table build failed: ") + cudaGetErrorString(e);
         return MIRGE_E_CUDA;
     }
@@ -961,12 +962,8 @@ static int annotate_impl(mirge_ctx *ctx)
         if (tail_skip && r >= 3 && rs.polyT && r + 1 < nrounds) { todo_out = ctx->d_todo_long; n_out = n_past; }
         if (tail_skip && r >= 4 && ROUNDS[r - 1].polyT) { todo_in = ctx->d_todo_long; n_in = n_past; }
         ProfScope ps(ctx, KID_K2_ROUND0 + r);
-        const bool eight = !(ctx->force_slow & 0x4000);    // 8 CTAs/SM measured faster for both pair rounds (0.57 vs 0.94 ms, 0.81 vs 1.19 ms)
-        if (R.ngap > 0 && eight)                            // short queries go through the pair-of-pieces tables
+        if (R.ngap > 0)                                     // short queries go through the pair-of-pieces tables
             k2_round_pairs8<W><<<148 * K2_CTAS, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
-                                                      ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
-        else if (R.ngap > 0)
-            k2_round_pairs<W><<<148 * K2_CTAS, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,
                                                       ctx->d_round_stats + r, ctx->d_round_stats + MIRGE_N_ROUNDS + r);
         else if (rs.param > 0 && rs.lib == MIRGE_LIB_MIRNA) // several seeds over consecutive table sizes: balance them
             k2_round_balanced<W><<<148 * K2_CTAS, 128, 0, st>>>(A, todo_in, n_in, todo_out, n_out, L, R,

@@ -18,6 +18,7 @@
 #ifndef K2_CTAS
 #define K2_CTAS 8       // resident CTAs per SM of the round kernels (64 registers); the grid is one wave of them
 #endif
+#define K2_CTAS_W4 5    // four-word sequences (reads of 65..128 nt): 96 registers without spills instead of 64 with 240 bytes spilled
 
 struct LibView {
     const u64 *seq;        // 2-bit packed concatenation (zero padded by >= 5 words)
@@ -235,7 +236,7 @@ __device__ __forceinline__ void k2_flush(const u32 *buf, u32 n, u32 *__restrict_
 // GAP: rounds whose library carries pair-of-pieces tables for their mismatch budget (GapSet above); queries whose
 // region a set serves take the m(m-1)/2 pair look-ups instead of the e + 1 classic seeds.
 #define K2_ROUND_NAME k2_round
-#define K2_LAUNCH_BOUNDS __launch_bounds__(128, K2_CTAS)
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, (W == 2 ? K2_CTAS : K2_CTAS_W4))
 #define K2_BAL 0
 #define K2_GAP 0
 #include "k2_round.inc"
@@ -244,7 +245,7 @@ __device__ __forceinline__ void k2_flush(const u32 *buf, u32 n, u32 *__restrict_
 #undef K2_BAL
 #undef K2_GAP
 #define K2_ROUND_NAME k2_round_balanced
-#define K2_LAUNCH_BOUNDS __launch_bounds__(128, K2_CTAS)
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, (W == 2 ? K2_CTAS : K2_CTAS_W4))
 #define K2_BAL 1
 #define K2_GAP 0
 #include "k2_round.inc"
@@ -252,17 +253,8 @@ __device__ __forceinline__ void k2_flush(const u32 *buf, u32 n, u32 *__restrict_
 #undef K2_LAUNCH_BOUNDS
 #undef K2_BAL
 #undef K2_GAP
-#define K2_ROUND_NAME k2_round_pairs
-#define K2_LAUNCH_BOUNDS __launch_bounds__(128)
-#define K2_BAL 1
-#define K2_GAP 1
-#include "k2_round.inc"
-#undef K2_ROUND_NAME
-#undef K2_LAUNCH_BOUNDS
-#undef K2_BAL
-#undef K2_GAP
 #define K2_ROUND_NAME k2_round_pairs8
-#define K2_LAUNCH_BOUNDS __launch_bounds__(128, K2_CTAS)
+#define K2_LAUNCH_BOUNDS __launch_bounds__(128, (W == 2 ? K2_CTAS : K2_CTAS_W4))
 #define K2_BAL 1
 #define K2_GAP 1
 #include "k2_round.inc"

@@ -6,7 +6,7 @@ the 25 M-read workload is generated once (about 8 s), every variant then costs t
         argv[5] pair-seed thresholds to run the K2 modes under (MIRGE_OPT_PAIR_SEEDS; default: the library default)
     mode bits: 1 all-column search for every read, 2 literal DP, 4 prefilter off, 0x100 no count updates (diagnostic),
     0x200 classification only (diagnostic), 0x800 count cache off,
-    0x4000 pair-seed rounds swap their register budget (8 CTAs/SM <-> natural)
+    0x1000 (K2) no poly-T bypass
 Diagnostic modes give wrong tables on purpose; they only attribute time."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

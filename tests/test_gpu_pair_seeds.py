@@ -10,10 +10,12 @@ from test_gpu_parity import _compare, _load_libs, _oracle_run
 pytestmark = pytest.mark.gpu
 
 
-def _engine_run(world, fqs, adapter, pair_seeds, max_unique=1 << 20, **kw):
+def _engine_run(world, fqs, adapter, pair_seeds, max_unique=1 << 20, debug=0, max_read_len=64, **kw):
     from mirge_b200.engine import Engine, LIB_IDS
-    e = Engine(len(fqs), False, max_unique, 64)
+    e = Engine(len(fqs), False, max_unique, max_read_len)
     e.set_adapter(adapter, **kw)
+    if debug:
+        e.set_trim_mode(debug)
     e.pair_seeds(pair_seeds)                 # read when the libraries are loaded
     _load_libs(e, world, LIB_IDS)
     for s, fq in enumerate(fqs):
@@ -59,10 +61,27 @@ def test_short_queries_with_and_without_pair_tables(small_world, oracle_mod, pai
     assert int((e.export_unique()['round_of'] == 9).sum()) > 100        # the isomiR round (-v 2) did find placements
 
 
+def test_short_queries_four_word_kernels(small_world, oracle_mod):
+    """The same with the 128-nt (four-word) instantiation of the round kernels."""
+    rng = np.random.default_rng(22)
+    fq = _fq(short_fragments(small_world, rng, 1500, 16, 40))
+    o = _oracle_run(oracle_mod, small_world, [fq], 'none')
+    e = _engine_run(small_world, [fq], 'none', 1, max_read_len=128)
+    _compare(oracle_mod, o, e)
+
+
 def test_whole_workload_with_pair_tables_everywhere(small_world, oracle_mod):
     fq = small_world.fastq(200000, seed=1234).tobytes()
     o = _oracle_run(oracle_mod, small_world, [fq], ILLUMINA)
     e = _engine_run(small_world, [fq], ILLUMINA, 1)
+    _compare(oracle_mod, o, e)
+
+
+def test_list_routing_does_not_change_results(small_world, oracle_mod):
+    """Debug bit 0x1000 sends every miss through the poly-T round instead of past it: same tables."""
+    fq = small_world.fastq(100000, seed=77).tobytes()
+    o = _oracle_run(oracle_mod, small_world, [fq], ILLUMINA)
+    e = _engine_run(small_world, [fq], ILLUMINA, 16, debug=0x1000)
     _compare(oracle_mod, o, e)
 
 
