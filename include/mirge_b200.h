@@ -140,6 +140,11 @@ int mirge_genome_pass_ids(mirge_ctx *ctx, uint64_t n, const uint32_t *ids, int m
  * tables only shorten the candidate lists -- the alignments reported are the same. */
 enum { MIRGE_OPT_ANNOTATE_WHILE_FEEDING = 1, MIRGE_OPT_PAIR_SEEDS = 2 };
 int mirge_set_option(mirge_ctx *ctx, int option, int value);
+/* Which pair-of-pieces seed sets mirge_load_library builds for a library of `total`
+ * bases in slot lib_id under MIRGE_OPT_PAIR_SEEDS = pair_seeds: up to four rows of
+ * {pieces, piece length, shortest region served, longest region served} in out16
+ * (may be NULL); returns the number of rows.  Host arithmetic only, no device call. */
+int mirge_pair_seed_plan(int lib_id, uint64_t total, int pair_seeds, int *out16);
 
 /* -- stage 3: tallies ----------------------------------------------------- */
 

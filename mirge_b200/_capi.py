@@ -45,6 +45,7 @@ _SIGS = {
     'mirge_genome_pass_ids': (C.c_int, [ctx_p, u64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     'mirge_annotate': (C.c_int, [ctx_p]),
     'mirge_set_option': (C.c_int, [ctx_p, C.c_int, C.c_int]),
+    'mirge_pair_seed_plan': (C.c_int, [C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int)]),
     'mirge_tally': (C.c_int, [ctx_p]),
     'mirge_export_unique': (C.c_int, [ctx_p, u64, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     'mirge_export_tables': (C.c_int, [ctx_p, vp, vp, vp, vp, vp, vp]),

@@ -624,12 +624,26 @@ static int build_gap_set(mirge_ctx *ctx, DevLib &l, const LibView &L, int m, int
     return MIRGE_OK;
 }
 
-// Which regions a pair set should serve: those where the classic seeds (e + 1 pieces, longest table that fits) are
-// expected to offer at least `ctx->pair_seeds` candidates per query and clearly more than the pair tables do
-// (pair_seeds == 1: every region the set can serve).  Expected counts assume a random library.
-static int plan_gap_sets(mirge_ctx *ctx, DevLib &l, const LibView &L, int lib_id, const std::vector<int> &ks)
+// plain seed lengths of a library slot (k-mer CSR tables)
+static std::vector<int> seed_lengths_for(int lib_id, u64 total)
 {
-    if (ctx->pair_seeds <= 0) return MIRGE_OK;
+    // the miRNA library serves the 3-seed isomiR round on reads as short as 13 nt (k = 4..8); the big mRNA library
+    // gets a 12-mer table.  The longest seed a read allows: every extra base divides the candidates to verify by four
+    if (lib_id == MIRGE_LIB_MIRNA) return {4, 5, 6, 7, 8};
+    if (total >= (1u << 20)) return {8, 9, 10, 11, 12};
+    return {8, 9, 10, 11};
+}
+
+// Which pair sets a library gets, and which region lengths each serves: those where the classic seeds (e + 1 pieces,
+// longest table that fits) are expected to offer at least `pair_seeds` candidates per query and clearly more than the
+// pair tables do (pair_seeds == 1: every region the set can serve; 0: none).  Expected counts assume a random library.
+// Host arithmetic only (mirge_pair_seed_plan exposes it to the CPU tests).  Rows: {m, pl, rg_lo, rg_hi}.
+struct GapPlanRow { int m, pl, rg_lo, rg_hi; };
+static std::vector<GapPlanRow> plan_gap_rows(int lib_id, u64 total, int pair_seeds)
+{
+    std::vector<GapPlanRow> rows;
+    if (pair_seeds <= 0 || lib_id < 0 || lib_id >= MIRGE_N_LIBS || lib_id == MIRGE_LIB_GENOME) return rows;
+    const std::vector<int> ks = seed_lengths_for(lib_id, total);
     for (int e = 1; e <= 2; e++) {
         bool used = false;
         for (int r = 0; r < MIRGE_N_ROUNDS; r++) if (ROUNDS[r].lib == lib_id && ROUNDS[r].param == e) used = true;
@@ -638,24 +652,41 @@ static int plan_gap_sets(mirge_ctx *ctx, DevLib &l, const LibView &L, int lib_id
         const int pls[2] = {m == 4 ? 3 : 5, m == 4 ? 4 : 6};
         for (int x = 0; x < 2; x++) {
             const int pl = pls[x], lo = m * pl, hi_max = x == 0 ? m * pls[1] - 1 : 23;
-            if ((u64)l.total < (u64)lo) continue;
-            const double pair_c = (double)npairs * l.total / (double)(1ull << (4 * pl));
-            auto classic_k = [&](int rg) { int kc = -1; for (int k : ks) if (k <= rg / (e + 1) && (u64)k <= l.total) kc = k; return kc; };
+            if (total < (u64)lo) continue;
+            const double pair_c = (double)npairs * (double)total / (double)(1ull << (4 * pl));
+            auto classic_k = [&](int rg) { int kc = -1; for (int k : ks) if (k <= rg / (e + 1) && (u64)k <= total) kc = k; return kc; };
             int s_lo = -1, s_hi = -1;
             for (int rg = lo; rg <= hi_max; rg++) {
                 const int kc = classic_k(rg);
-                const double classic_c = kc < 0 ? 0.0 : (double)(e + 1) * l.total / (double)(1ull << (2 * kc));
-                const bool serve = ctx->pair_seeds == 1 || (classic_c >= (double)ctx->pair_seeds && classic_c > 1.5 * pair_c + 2.0);
+                const double classic_c = kc < 0 ? 0.0 : (double)(e + 1) * (double)total / (double)(1ull << (2 * kc));
+                const bool serve = pair_seeds == 1 || (classic_c >= (double)pair_seeds && classic_c > 1.5 * pair_c + 2.0);
                 if (serve) { if (s_lo < 0) s_lo = rg; s_hi = rg; }
                 else if (s_lo >= 0) break;
             }
-            if (s_lo < 0 || l.ngap >= 4) continue;
+            if (s_lo < 0 || rows.size() >= 4) continue;
             // regions no classic table fits (below 16 bases, only with a non-default min_length) would scan every offset:
             // a set that exists anyway takes them too
             while (s_lo > lo && classic_k(s_lo - 1) < 0) s_lo--;
-            int rc = build_gap_set(ctx, l, L, m, pl, s_lo, s_hi);
-            if (rc) return rc;
+            rows.push_back({m, pl, s_lo, s_hi});
         }
+    }
+    return rows;
+}
+
+int mirge_pair_seed_plan(int lib_id, uint64_t total, int pair_seeds, int *out16)
+{
+    const std::vector<GapPlanRow> rows = plan_gap_rows(lib_id, total, pair_seeds);
+    for (size_t i = 0; i < rows.size() && out16; i++) {
+        out16[4 * i] = rows[i].m; out16[4 * i + 1] = rows[i].pl; out16[4 * i + 2] = rows[i].rg_lo; out16[4 * i + 3] = rows[i].rg_hi;
+    }
+    return (int)rows.size();
+}
+
+static int plan_gap_sets(mirge_ctx *ctx, DevLib &l, const LibView &L, int lib_id)
+{
+    for (const GapPlanRow &g : plan_gap_rows(lib_id, l.total, ctx->pair_seeds)) {
+        int rc = build_gap_set(ctx, l, L, g.m, g.pl, g.rg_lo, g.rg_hi);
+        if (rc) return rc;
     }
     return MIRGE_OK;
 }
@@ -728,12 +759,7 @@ static int load_library_impl(mirge_ctx *ctx, int lib_id, int n_refs, const char 
         CK(cudaGetLastError());
         return MIRGE_OK;
     }
-    // seed tables: the miRNA library serves the 3-seed isomiR round on reads as
-    // short as 13 nt (k = 4..8); the big mRNA library gets a 12-mer table.
-    std::vector<int> ks;
-    if (lib_id == MIRGE_LIB_MIRNA) ks = {4, 5, 6, 7, 8};
-    else if (total >= (1u << 20)) ks = {8, 9, 10, 11, 12};
-    else ks = {8, 9, 10, 11};   // the longest seed a read allows: every extra base divides the candidates to verify by four
+    const std::vector<int> ks = seed_lengths_for(lib_id, total);
     for (int k : ks) {
         if ((u64)k > total) continue;
         const u64 nb = 1ull << (2 * k);
@@ -763,7 +789,7 @@ static int load_library_impl(mirge_ctx *ctx, int lib_id, int n_refs, const char 
     CK(cudaStreamSynchronize(st));
     cudaFree(d_ascii);
     CK(cudaGetLastError());
-    { int rc = plan_gap_sets(ctx, l, L, lib_id, ks); if (rc) return rc; }
+    { int rc = plan_gap_sets(ctx, l, L, lib_id); if (rc) return rc; }
     { int rc = annot_clear(ctx); if (rc) return rc; }          // a library changed: every sequence is looked at again
     ctx->annotated = false; ctx->tallied = false;
     return MIRGE_OK;
