@@ -258,7 +258,7 @@ __host__ __device__ __forceinline__ int k1_trim_fast(const PSeq<W> &p, int n, co
 }
 
 // Per-thread variant of k1_match_fast for the reads the windowed version could not
-// settle (walks that leave the 16-column ring, full-length inexact occurrences far
+// settle (walks that leave the 8-column ring, full-length inexact occurrences far
 // from the read end): the same bit-vector algorithm, but the vectors of EVERY column
 // are kept (thread-local arrays), so nothing is out of reach.  Not warp-collective;
 // run by converged threads when the slow queue is drained.
